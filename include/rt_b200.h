@@ -1,0 +1,244 @@
+/*
+ * rt_b200.h — C ABI of the B200-native path-tracing hot path.
+ *
+ * This is the drop-in boundary for the reference's render loop.  The reference
+ * (mu-lambda/mu-lambda-raytracer, Rust) has no FFI; the seam this library
+ * replaces is
+ *
+ *     Renderer::new_with_rng(camera, world, background, params, tracer, rng)
+ *     Renderer::render(logger) -> Vec<Vec<RGB>>            src/raytrace.rs:151-186
+ *
+ * called from exactly one place, do_tracing (src/main.rs:147-157).  Because the
+ * reference's world is an opaque Box<dyn Hittable> (src/worlds.rs:18,
+ * src/hittable.rs:33-35), the host hands the library a *scene description*
+ * (RtSceneDesc): the reference's object tree written down node for node in
+ * construction order, all values f64 exactly as the Rust code holds them.
+ *
+ * Conventions: plain-old-data structs, caller-owned memory, `int` status
+ * returns (0 = RT_OK), rt_last_error() for the message, no exceptions and no
+ * callbacks from device threads.  There is NO CPU fallback: every compute
+ * entry point returns RT_ERR_NO_DEVICE when no CUDA device is usable.
+ */
+#ifndef RT_B200_H
+#define RT_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define RT_B200_ABI_VERSION 1
+
+/* ---- status codes (replace the reference's unwrap()/panic!()) ---- */
+enum {
+    RT_OK = 0,
+    RT_ERR_INVALID = 1,    /* bad argument / malformed description */
+    RT_ERR_NO_DEVICE = 2,  /* no usable CUDA device: there is no CPU path */
+    RT_ERR_CUDA = 3,       /* a CUDA call failed; see rt_last_error() */
+    RT_ERR_UNSUPPORTED = 4 /* description uses a construct the device path cannot flatten */
+};
+
+/* ---- scene description: mirrors the reference's trait-object tree ---- */
+
+/* node kinds: one per Hittable impl of the reference */
+enum {
+    RT_NODE_SPHERE = 1,    /* shapes.rs:26-82      f = cx,cy,cz,radius (radius may be negative) */
+    RT_NODE_XYRECT = 2,    /* shapes.rs:92-108     f = x0,x1,y0,y1,z */
+    RT_NODE_XZRECT = 3,    /* shapes.rs:117-133    f = x0,x1,z0,z1,y */
+    RT_NODE_YZRECT = 4,    /* shapes.rs:142-158    f = y0,y1,z0,z1,x */
+    RT_NODE_BLOCK = 5,     /* shapes.rs:166-198    f = p0x,p0y,p0z,p1x,p1y,p1z */
+    RT_NODE_TRANSLATE = 6, /* transforms.rs:20-42  f = ox,oy,oz; child = wrapped node */
+    RT_NODE_ROTATE = 7,    /* transforms.rs:51-142 axis = 0/1/2, f[0] = angle in degrees; child */
+    RT_NODE_MEDIUM = 8,    /* volumes.rs:7-65      f[0] = density d; material = its Isotropic; child = boundary */
+    RT_NODE_BVH = 9,       /* bhv.rs:85-101        children[first_child .. +child_count], insertion order */
+    RT_NODE_LIST = 10      /* hittable.rs:37-68    children[first_child .. +child_count], insertion order */
+};
+
+typedef struct RtNode {
+    int32_t kind;
+    int32_t material;    /* index into materials, -1 when the kind has none */
+    int32_t first_child; /* TRANSLATE/ROTATE/MEDIUM: child node index; BVH/LIST: offset into children[] */
+    int32_t child_count; /* BVH/LIST only */
+    int32_t axis;        /* ROTATE only */
+    int32_t reserved;
+    double f[8];
+} RtNode;
+
+enum {
+    RT_MAT_LAMBERTIAN = 1,    /* materials.rs:14-34   texture */
+    RT_MAT_METAL = 2,         /* materials.rs:36-61   albedo, fuzz */
+    RT_MAT_DIELECTRIC = 3,    /* materials.rs:70-106  ior */
+    RT_MAT_DIFFUSE_LIGHT = 4, /* materials.rs:108-127 texture */
+    RT_MAT_ISOTROPIC = 5      /* volumes.rs:67-83     texture */
+};
+
+typedef struct RtMaterial {
+    int32_t kind;
+    int32_t texture; /* index into textures, -1 when unused */
+    double albedo[3];
+    double fuzz;
+    double ior;
+} RtMaterial;
+
+enum {
+    RT_TEX_SOLID = 1,   /* textures.rs:8-26     color */
+    RT_TEX_CHECKER = 2, /* textures.rs:28-49    odd, even = texture indices */
+    RT_TEX_NOISE = 3,   /* textures.rs:151-167  perlin = table index, scale */
+    RT_TEX_IMAGE = 4    /* image_texture.rs     image = image index */
+};
+
+typedef struct RtTexture {
+    int32_t kind;
+    int32_t a; /* CHECKER: odd texture; NOISE: perlin table; IMAGE: image */
+    int32_t b; /* CHECKER: even texture */
+    int32_t reserved;
+    double color[3];
+    double scale;
+} RtTexture;
+
+#define RT_PERLIN_POINTS 1024 /* textures.rs:51 */
+
+typedef struct RtPerlin {
+    double ranvec[RT_PERLIN_POINTS][3];
+    int32_t perm_x[RT_PERLIN_POINTS];
+    int32_t perm_y[RT_PERLIN_POINTS];
+    int32_t perm_z[RT_PERLIN_POINTS];
+} RtPerlin;
+
+typedef struct RtImage {
+    int32_t width, height;
+    const uint8_t* rgb; /* width*height*3, row 0 = top of the file, as image::RgbImage */
+} RtImage;
+
+enum { RT_BG_BLACK = 0, RT_BG_GRADIENT = 1 }; /* raytrace.rs:12-48 */
+
+typedef struct RtSceneDesc {
+    int32_t root; /* node index of what World::build returned */
+    int32_t background_kind;
+    double background_top[3];    /* GradientBackground.top    (raytrace.rs:13) */
+    double background_bottom[3]; /* GradientBackground.bottom (raytrace.rs:14) */
+    int32_t n_nodes, n_children, n_materials, n_textures, n_perlins, n_images;
+    const RtNode* nodes;
+    const int32_t* children;
+    const RtMaterial* materials;
+    const RtTexture* textures;
+    const RtPerlin* perlins;
+    const RtImage* images;
+} RtSceneDesc;
+
+/* the seven inputs of Camera::new (camera.rs:15-23) */
+typedef struct RtCamera {
+    double lookfrom[3], lookat[3], vup[3];
+    double vfov_deg;
+    double aspect_ratio; /* the FLAG ratio, not W/H (main.rs:197) */
+    double aperture;
+    double focus_dist;
+} RtCamera;
+
+enum { RT_PIPELINE_AUTO = 0, RT_PIPELINE_MEGAKERNEL = 1, RT_PIPELINE_WAVEFRONT = 2 };
+
+/* RenderingParams (raytrace.rs:50-55) + max_depth (main.rs:72) + device-side knobs */
+typedef struct RtParams {
+    int32_t width, height;
+    int32_t samples_per_pixel; /* spp of the WHOLE image (used by the tonemap divisor) */
+    int32_t max_depth;
+    uint64_t seed;             /* key of the Philox render streams */
+    int32_t sample_begin;      /* this call renders samples [sample_begin, sample_begin+sample_count) */
+    int32_t sample_count;      /* 0 = all of samples_per_pixel */
+    int32_t pipeline;          /* RT_PIPELINE_* */
+    int32_t device;            /* CUDA ordinal, -1 = current */
+} RtParams;
+
+typedef struct RtScene RtScene; /* opaque: flattened scene resident on one device */
+
+/* closest-hit record of the test entry point (mirrors hittable.rs:7-15) */
+typedef struct RtHit {
+    float t;
+    float p[3];
+    float normal[3];
+    float u, v;
+    int32_t front_face;
+    int32_t material; /* index into desc.materials; -1 = miss */
+    int32_t prim;     /* device primitive id, -1 = miss */
+} RtHit;
+
+/* counters of one render call (rays = path segments traced) */
+typedef struct RtStats {
+    uint64_t paths;
+    uint64_t rays;
+    double device_ms; /* CUDA-event time of the timed region */
+    int32_t kernel_launches;
+    int32_t pipeline_used;
+} RtStats;
+
+typedef void (*RtProgressFn)(int done, int total, void* user);
+
+const char* rt_last_error(void);
+int rt_abi_version(void);
+int rt_device_count(void);
+
+/* canonical SHA-256 of a description (values as f64, construction order) */
+int rt_scene_hash(const RtSceneDesc* desc, uint8_t out[32]);
+
+/* flatten + build the device BVH + upload.  Replaces World::build's result + World::background. */
+int rt_scene_create(const RtSceneDesc* desc, int device, RtScene** out);
+void rt_scene_destroy(RtScene* scene);
+int rt_scene_info(const RtScene* scene, int32_t* n_prims, int32_t* n_bvh_nodes, int32_t* n_media, int64_t* device_bytes);
+
+/*
+ * Renderer::new_with_rng + render (raytrace.rs:151-186) with HOST buffers.
+ *   accum_rgb: optional, 3*W*H floats, sum of sample radiance (not divided by spp)
+ *   rgb:       optional, 3*W*H int32 in 0..=255 after to_rgb (raytrace.rs:59-68);
+ *              row j = 0 is the BOTTOM row, exactly like the reference's Vec<Vec<RGB>>.
+ * Blocking; cb is invoked on the calling host thread only.
+ */
+int rt_render(const RtScene* scene, const RtCamera* cam, const RtParams* params, float* accum_rgb,
+              int32_t* rgb, RtProgressFn cb, void* user, RtStats* stats);
+
+/*
+ * Same work with DEVICE buffers (for sharded multi-GPU use: the caller owns the
+ * accumulation buffer, reduces it across ranks, then tonemaps on the root).
+ * d_accum_rgb: 3*W*H floats on scene's device, ADDED to (caller zeroes it).
+ * stream: a cudaStream_t passed as void* (NULL = default stream).  Asynchronous
+ * unless stats != NULL (then it synchronises to fill device_ms / rays).
+ */
+int rt_render_accumulate_device(const RtScene* scene, const RtCamera* cam, const RtParams* params,
+                                float* d_accum_rgb, void* stream, RtStats* stats);
+int rt_tonemap_device(const float* d_accum_rgb, int32_t* d_rgb, int32_t n_pixels, int32_t samples_per_pixel,
+                      int device, void* stream);
+
+/*
+ * Hittable::hit for a batch of rays (test entry point, SURVEY §8c level 2).
+ *   node: index of a node of the description the scene was created from; the
+ *         closest hit of that subtree is returned (root = whole world, media excluded
+ *         unless node is itself a MEDIUM, in which case `t` = entry and `u` = exit of
+ *         the clipped boundary interval and no free-flight sampling is done).
+ *   rays: N x 8 floats: origin xyz, direction xyz (NOT normalised), t_min, t_max.
+ */
+int rt_intersect_batch(const RtScene* scene, int32_t node, const float* rays, int64_t n, RtHit* out);
+
+/* ---- host side above the ABI: worlds.rs restated against the description ---- */
+
+typedef struct RtWorldInfo {
+    double lookfrom[3], lookat[3];
+    double vfov_deg;
+    int32_t background_kind;
+    int32_t needs_earthmap;
+    int32_t uses_rng;
+} RtWorldInfo;
+
+int rt_world_count(void);
+const char* rt_world_name(int index);
+int rt_world_info(const char* name, RtWorldInfo* out);
+/* World::build with rng = Pcg64::seed_from_u64(seed) (main.rs:185, rngator.rs:27-31).
+ * earth_rgb may be NULL unless the world needs it.  *n_draws (optional) = next_u64 calls consumed. */
+int rt_world_build(const char* name, uint64_t seed, const uint8_t* earth_rgb, int32_t earth_w, int32_t earth_h,
+                   RtSceneDesc** out, uint64_t* n_draws);
+void rt_scene_desc_free(RtSceneDesc* desc);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* RT_B200_H */
