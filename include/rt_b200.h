@@ -148,7 +148,9 @@ typedef struct RtParams {
     int32_t sample_begin;      /* this call renders samples [sample_begin, sample_begin+sample_count) */
     int32_t sample_count;      /* 0 = all of samples_per_pixel */
     int32_t pipeline;          /* RT_PIPELINE_* */
-    int32_t device;            /* CUDA ordinal, -1 = current */
+    int32_t device;            /* ignored: a scene lives on the device it was created on */
+    int32_t samples_per_item;  /* tuning: consecutive samples one GPU thread integrates (0 = auto) */
+    int32_t reserved;
 } RtParams;
 
 typedef struct RtScene RtScene; /* opaque: flattened scene resident on one device */
@@ -218,6 +220,21 @@ int rt_tonemap_device(const float* d_accum_rgb, int32_t* d_rgb, int32_t n_pixels
  *   rays: N x 8 floats: origin xyz, direction xyz (NOT normalised), t_min, t_max.
  */
 int rt_intersect_batch(const RtScene* scene, int32_t node, const float* rays, int64_t n, RtHit* out);
+
+/*
+ * Texture::value (textures.rs:4-6) for a batch (test entry point).
+ *   texture: index into desc.textures; uvp: N x 5 floats (u, v, p.x, p.y, p.z); out: N x 3 floats.
+ */
+int rt_texture_value_batch(const RtScene* scene, int32_t texture, const float* uvp, int64_t n, float* out_rgb);
+
+/*
+ * Camera::get_ray + the pixel jitter of render_pixel (camera.rs:40-48, raytrace.rs:191-192) for a batch of
+ * (pixel, sample) pairs (test entry point).  pixel = j*width + i with j = 0 the bottom row.
+ *   out_rays:   N x 6 floats, origin xyz + direction xyz (not normalised)
+ *   out_sample: N x 4 floats, the four uniforms used: jitter x, jitter y, lens disk x, lens disk y
+ */
+int rt_generate_rays(const RtCamera* cam, const RtParams* params, const int32_t* pixel, const int32_t* sample,
+                     int64_t n, float* out_rays, float* out_sample);
 
 /* ---- host side above the ABI: worlds.rs restated against the description ---- */
 

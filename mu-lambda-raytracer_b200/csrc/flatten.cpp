@@ -1,0 +1,494 @@
+// Scene description -> flat device layout.
+//
+// Replaces the pointer tree the reference traverses (Box<dyn Hittable> of HittableList / BHV / Translate /
+// Rotate / ConstantMedium; src/hittable.rs:37-68, src/bhv.rs:85-165, src/transforms.rs, src/volumes.rs):
+//   * Translate/Rotate chains are composed into one rigid instance per primitive; spheres are moved to
+//     world space outright (a rigid transform of a sphere is a sphere), boxes keep an object-space record.
+//   * HittableList and BHV are transparent: all surface primitives go into ONE SAH-built BVH (the reference's
+//     random-axis median split, bhv.rs:122-145, only matters for its RNG consumption, which worlds.cpp replays).
+//   * ConstantMedium nodes are pulled out into a short media list evaluated after the surface search.
+#include "flatten.h"
+
+#include <algorithm>
+#include <cmath>
+#include <cstring>
+#include <limits>
+#include <map>
+
+namespace rtb {
+namespace {
+
+const double kPi = 3.14159265358979323846264338327950288;
+
+struct M3 {
+    double m[9];
+    static M3 identity() { return M3{{1, 0, 0, 0, 1, 0, 0, 0, 1}}; }
+    M3 operator*(const M3& o) const {
+        M3 r{};
+        for (int i = 0; i < 3; ++i)
+            for (int j = 0; j < 3; ++j) {
+                double s = 0;
+                for (int k = 0; k < 3; ++k) s += m[3 * i + k] * o.m[3 * k + j];
+                r.m[3 * i + j] = s;
+            }
+        return r;
+    }
+    M3 transposed() const { return M3{{m[0], m[3], m[6], m[1], m[4], m[7], m[2], m[5], m[8]}}; }
+    void apply(const double v[3], double out[3]) const {
+        for (int i = 0; i < 3; ++i) out[i] = m[3 * i] * v[0] + m[3 * i + 1] * v[1] + m[3 * i + 2] * v[2];
+    }
+};
+
+// matrix of Rotate::rotate (object -> world), transforms.rs:116-124
+M3 rotation_of(int axis, double degrees) {
+    int a1 = axis, a2 = (a1 + 1) % 3, a0 = (a1 + 2) % 3;
+    double theta = degrees * kPi / 180.0;
+    double s = std::sin(theta), c = std::cos(theta);
+    M3 r{};
+    r.m[3 * a1 + a1] = 1.0;
+    r.m[3 * a0 + a0] = c, r.m[3 * a0 + a2] = s;
+    r.m[3 * a2 + a0] = -s, r.m[3 * a2 + a2] = c;
+    return r;
+}
+
+struct Wrapper {
+    bool is_rotate;
+    M3 rot;         // rotate: its matrix
+    double off[3];  // translate: its offset
+};
+
+struct Box3 {
+    double lo[3], hi[3];
+    void reset() {
+        for (int i = 0; i < 3; ++i) lo[i] = std::numeric_limits<double>::infinity(), hi[i] = -lo[i];
+    }
+    void grow(const double p[3]) {
+        for (int i = 0; i < 3; ++i) lo[i] = std::min(lo[i], p[i]), hi[i] = std::max(hi[i], p[i]);
+    }
+    void grow(const Box3& b) { grow(b.lo), grow(b.hi); }
+    double area() const {
+        double d[3] = {hi[0] - lo[0], hi[1] - lo[1], hi[2] - lo[2]};
+        return 2.0 * (d[0] * d[1] + d[1] * d[2] + d[2] * d[0]);
+    }
+};
+
+float round_down(double x) {
+    float f = (float)x;
+    return (double)f > x ? std::nextafterf(f, -std::numeric_limits<float>::infinity()) : f;
+}
+float round_up(double x) {
+    float f = (float)x;
+    return (double)f < x ? std::nextafterf(f, std::numeric_limits<float>::infinity()) : f;
+}
+
+class Flattener {
+   public:
+    Flattener(const RtSceneDesc* d, FlatScene& out, std::string& err) : d(d), out(out), err(err) {}
+    const RtSceneDesc* d;
+    FlatScene& out;
+    std::string& err;
+    std::vector<Box3> prim_box;
+    int status = RT_OK;
+
+    bool fail(int code, const std::string& msg) {
+        if (status == RT_OK) status = code, err = msg;
+        return false;
+    }
+
+    std::map<std::vector<double>, int> inst_cache;  // one instance record per distinct wrapper chain
+
+    int instance_of(const std::vector<Wrapper>& chain) {
+        if (chain.empty()) return 0;
+        std::vector<double> key;
+        for (const Wrapper& w : chain) {
+            key.push_back(w.is_rotate ? 1.0 : 0.0);
+            key.insert(key.end(), w.rot.m, w.rot.m + 9);
+            key.insert(key.end(), w.off, w.off + 3);
+        }
+        auto found = inst_cache.find(key);
+        if (found != inst_cache.end()) return found->second;
+        M3 R = M3::identity();
+        double T[3] = {0, 0, 0};
+        for (const Wrapper& w : chain) {
+            if (w.is_rotate) {
+                R = R * w.rot;
+            } else {
+                double t[3];
+                R.apply(w.off, t);
+                for (int i = 0; i < 3; ++i) T[i] += t[i];
+            }
+        }
+        // how the two outermost wrappers re-face-forward the normal (see DInstance in rt_types.h)
+        M3 m1 = chain[0].is_rotate ? chain[0].rot.transposed() : M3::identity();
+        M3 m2 = M3::identity();
+        if (chain.size() >= 2 && chain[1].is_rotate) {
+            M3 r1 = chain[0].is_rotate ? chain[0].rot : M3::identity();
+            m2 = r1 * chain[1].rot.transposed() * r1.transposed();
+        }
+        DInstance di{};
+        for (int i = 0; i < 9; ++i) di.rot[i] = (float)R.m[i], di.m1[i] = (float)m1.m[i], di.m2[i] = (float)m2.m[i];
+        for (int i = 0; i < 3; ++i) di.trans[i] = (float)T[i];
+        out.inst.push_back(di);
+        inst_R.push_back(R);
+        inst_T.push_back({T[0], T[1], T[2]});
+        if (out.inst.size() > PRIM_INST_MASK) fail(RT_ERR_UNSUPPORTED, "too many transform instances");
+        inst_cache[key] = (int)out.inst.size();
+        return (int)out.inst.size();  // index + 1
+    }
+    std::vector<M3> inst_R;
+    struct T3 {
+        double v[3];
+    };
+    std::vector<T3> inst_T;
+
+    bool valid_material(int m) { return m >= 0 && m < d->n_materials; }
+
+    // build the device record of one primitive node under `chain`; false if the node is not a primitive
+    bool make_prim(int node, const std::vector<Wrapper>& chain, DPrim& p, Box3& box) {
+        const RtNode& n = d->nodes[node];
+        std::memset(&p, 0, sizeof p);
+        p.mat = n.material;
+        box.reset();
+        if (n.kind == RT_NODE_SPHERE) {
+            if (!valid_material(n.material)) return fail(RT_ERR_INVALID, "sphere without a material");
+            int inst = instance_of(chain);
+            double c[3] = {n.f[0], n.f[1], n.f[2]}, r = n.f[3];
+            if (inst) {
+                double cw[3];
+                inst_R[inst - 1].apply(c, cw);
+                for (int i = 0; i < 3; ++i) c[i] = cw[i] + inst_T[inst - 1].v[i];
+            }
+            p.meta = PRIM_SPHERE | ((uint32_t)inst << PRIM_INST_SHIFT);
+            for (int i = 0; i < 3; ++i) p.v[i] = (float)c[i];
+            p.v[3] = (float)r;
+            if (std::fabs(r) >= RTB_BIG_SPHERE_RADIUS) {
+                p.meta |= PRIM_BIG;
+                uint32_t idx = (uint32_t)out.big.size();
+                std::memcpy(&p.v[4], &idx, 4);
+                out.big.push_back(DBigSphere{{c[0], c[1], c[2]}, r});
+            }
+            double ar = std::fabs(r);
+            double a[3] = {c[0] - ar, c[1] - ar, c[2] - ar}, b[3] = {c[0] + ar, c[1] + ar, c[2] + ar};
+            box.grow(a), box.grow(b);
+            return true;
+        }
+        double lo[3], hi[3];
+        uint32_t rect_axis = 0;
+        if (n.kind == RT_NODE_XYRECT || n.kind == RT_NODE_XZRECT || n.kind == RT_NODE_YZRECT) {
+            // AARect::new (aarects.rs:31-43) incl. its one-sided normalisation of the second axis
+            int a0 = n.kind == RT_NODE_YZRECT ? 1 : 0;
+            int a1 = n.kind == RT_NODE_XYRECT ? 1 : 2;
+            int ap = 3 - a0 - a1;
+            lo[a0] = std::min(n.f[0], n.f[1]), hi[a0] = std::max(n.f[1], n.f[0]);
+            lo[a1] = n.f[2], hi[a1] = std::max(n.f[3], n.f[2]);
+            lo[ap] = hi[ap] = n.f[4];
+            rect_axis = (uint32_t)ap + 1;
+        } else if (n.kind == RT_NODE_BLOCK) {
+            for (int i = 0; i < 3; ++i) {
+                lo[i] = n.f[i], hi[i] = n.f[3 + i];
+                if (!(lo[i] <= hi[i])) return fail(RT_ERR_UNSUPPORTED, "Block corners must be ordered (p0 <= p1)");
+            }
+        } else {
+            return false;
+        }
+        if (!valid_material(n.material)) return fail(RT_ERR_INVALID, "rect/block without a material");
+        int inst = instance_of(chain);
+        p.meta = PRIM_BOX | ((uint32_t)inst << PRIM_INST_SHIFT) | (rect_axis << PRIM_RECT_SHIFT);
+        for (int i = 0; i < 3; ++i) p.v[i] = (float)lo[i], p.v[3 + i] = (float)hi[i];
+        for (int corner = 0; corner < 8; ++corner) {
+            double q[3] = {corner & 1 ? hi[0] : lo[0], corner & 2 ? hi[1] : lo[1], corner & 4 ? hi[2] : lo[2]};
+            if (inst) {
+                double w[3];
+                inst_R[inst - 1].apply(q, w);
+                for (int i = 0; i < 3; ++i) q[i] = w[i] + inst_T[inst - 1].v[i];
+            }
+            box.grow(q);
+        }
+        return true;
+    }
+
+    // resolve a medium boundary: wrappers down to exactly one primitive
+    bool make_boundary(int node, std::vector<Wrapper> chain, DPrim& p) {
+        for (int guard = 0; guard < 64; ++guard) {
+            if (node < 0 || node >= d->n_nodes) return fail(RT_ERR_INVALID, "medium boundary: bad node index");
+            const RtNode& n = d->nodes[node];
+            if (n.kind == RT_NODE_TRANSLATE) {
+                Wrapper w{false, M3::identity(), {n.f[0], n.f[1], n.f[2]}};
+                chain.push_back(w), node = n.first_child;
+            } else if (n.kind == RT_NODE_ROTATE) {
+                Wrapper w{true, rotation_of(n.axis, n.f[0]), {0, 0, 0}};
+                chain.push_back(w), node = n.first_child;
+            } else {
+                Box3 b;
+                if (make_prim(node, chain, p, b)) return true;
+                if (status != RT_OK) return false;
+                return fail(RT_ERR_UNSUPPORTED, "medium boundary must be a single sphere, rect or block (optionally translated/rotated)");
+            }
+        }
+        return fail(RT_ERR_INVALID, "medium boundary: transform chain too deep");
+    }
+
+    void walk(int node, std::vector<Wrapper>& chain, int depth) {
+        if (status != RT_OK) return;
+        if (node < 0 || node >= d->n_nodes) {
+            fail(RT_ERR_INVALID, "node index out of range");
+            return;
+        }
+        if (depth > 64) {
+            fail(RT_ERR_INVALID, "description nests deeper than 64 levels (cycle?)");
+            return;
+        }
+        const RtNode& n = d->nodes[node];
+        switch (n.kind) {
+            case RT_NODE_TRANSLATE: {
+                chain.push_back(Wrapper{false, M3::identity(), {n.f[0], n.f[1], n.f[2]}});
+                walk(n.first_child, chain, depth + 1);
+                chain.pop_back();
+                break;
+            }
+            case RT_NODE_ROTATE: {
+                if (n.axis < 0 || n.axis > 2) {
+                    fail(RT_ERR_INVALID, "rotate axis must be 0, 1 or 2");
+                    return;
+                }
+                chain.push_back(Wrapper{true, rotation_of(n.axis, n.f[0]), {0, 0, 0}});
+                walk(n.first_child, chain, depth + 1);
+                chain.pop_back();
+                break;
+            }
+            case RT_NODE_BVH:
+            case RT_NODE_LIST: {
+                if (n.first_child < 0 || n.child_count < 0 || n.first_child + n.child_count > d->n_children) {
+                    fail(RT_ERR_INVALID, "list/bvh child range out of bounds");
+                    return;
+                }
+                for (int i = 0; i < n.child_count; ++i) walk(d->children[n.first_child + i], chain, depth + 1);
+                break;
+            }
+            case RT_NODE_MEDIUM: {
+                if (!valid_material(n.material) || d->materials[n.material].kind != RT_MAT_ISOTROPIC) {
+                    fail(RT_ERR_INVALID, "medium needs an isotropic phase material");
+                    return;
+                }
+                if (!(n.f[0] > 0.0)) {
+                    fail(RT_ERR_INVALID, "medium density must be positive");
+                    return;
+                }
+                DMedium m{};
+                if (!make_boundary(n.first_child, chain, m.boundary)) return;
+                m.neg_inv_density = (float)(-1.0 / n.f[0]);
+                m.mat = n.material;
+                m.desc_node = node;
+                out.media.push_back(m);
+                if (out.media.size() > RTB_MAX_MEDIA) fail(RT_ERR_UNSUPPORTED, "more than 4 constant media in one scene");
+                break;
+            }
+            default: {
+                DPrim p;
+                Box3 b;
+                if (make_prim(node, chain, p, b)) {
+                    out.prims.push_back(p);
+                    out.prim_node.push_back(node);
+                    prim_box.push_back(b);
+                } else if (status == RT_OK) {
+                    fail(RT_ERR_INVALID, "unknown node kind");
+                }
+            }
+        }
+    }
+
+    // ---- SAH BVH over prim_box ----
+    std::vector<int> order;
+    static constexpr int kMaxLeaf = 4;
+
+    Box3 bounds_of(int begin, int end) const {
+        Box3 b;
+        b.reset();
+        for (int i = begin; i < end; ++i) b.grow(prim_box[order[i]]);
+        return b;
+    }
+
+    void build_node(int idx, int begin, int end, int depth) {
+        out.bvh_depth = std::max(out.bvh_depth, depth);
+        Box3 b = bounds_of(begin, end);
+        for (int i = 0; i < 3; ++i) out.nodes[idx].lo[i] = round_down(b.lo[i]), out.nodes[idx].hi[i] = round_up(b.hi[i]);
+        int n = end - begin;
+        double best_cost = std::numeric_limits<double>::infinity();
+        int best_axis = -1, best_split = -1;
+        if (n >= 2) {
+            double parent_area = std::max(b.area(), 1e-300);
+            std::vector<double> right_area(n);
+            for (int axis = 0; axis < 3; ++axis) {
+                std::stable_sort(order.begin() + begin, order.begin() + end, [&](int x, int y) {
+                    return prim_box[x].lo[axis] + prim_box[x].hi[axis] < prim_box[y].lo[axis] + prim_box[y].hi[axis];
+                });
+                Box3 acc;
+                acc.reset();
+                for (int i = n - 1; i >= 1; --i) {
+                    acc.grow(prim_box[order[begin + i]]);
+                    right_area[i] = acc.area();
+                }
+                acc.reset();
+                for (int i = 1; i < n; ++i) {
+                    acc.grow(prim_box[order[begin + i - 1]]);
+                    double cost = 1.0 + (acc.area() * i + right_area[i] * (n - i)) / parent_area;
+                    if (cost < best_cost) best_cost = cost, best_axis = axis, best_split = i;
+                }
+            }
+        }
+        bool leaf = n <= kMaxLeaf && (n < 2 || (double)n <= best_cost);
+        if (depth >= RTB_BVH_STACK - 2 && n <= 255) leaf = true;  // never outgrow the traversal stack
+        if (leaf) {
+            out.nodes[idx].a = begin, out.nodes[idx].b = n;
+            return;
+        }
+        std::stable_sort(order.begin() + begin, order.begin() + end, [&](int x, int y) {
+            return prim_box[x].lo[best_axis] + prim_box[x].hi[best_axis] < prim_box[y].lo[best_axis] + prim_box[y].hi[best_axis];
+        });
+        int left = (int)out.nodes.size();
+        out.nodes.push_back(DNode{}), out.nodes.push_back(DNode{});
+        out.nodes[idx].a = left, out.nodes[idx].b = 0;
+        build_node(left, begin, begin + best_split, depth + 1);
+        build_node(left + 1, begin + best_split, end, depth + 1);
+    }
+
+    void build_bvh() {
+        int n = (int)out.prims.size();
+        out.nodes.clear();
+        out.nodes.push_back(DNode{});
+        if (n == 0) {  // empty world: a leaf with no primitives
+            out.nodes[0].a = 0, out.nodes[0].b = 0;
+            return;
+        }
+        order.resize(n);
+        for (int i = 0; i < n; ++i) order[i] = i;
+        build_node(0, 0, n, 0);
+        std::vector<DPrim> p2(n);
+        std::vector<int32_t> n2(n);
+        for (int i = 0; i < n; ++i) p2[i] = out.prims[order[i]], n2[i] = out.prim_node[order[i]];
+        out.prims.swap(p2), out.prim_node.swap(n2);
+    }
+
+    bool tables() {
+        for (int i = 0; i < d->n_materials; ++i) {
+            const RtMaterial& m = d->materials[i];
+            DMaterial dm{};
+            dm.kind = m.kind, dm.tex = m.texture, dm.fuzz = (float)m.fuzz, dm.ior = (float)m.ior;
+            for (int k = 0; k < 3; ++k) dm.albedo[k] = (float)m.albedo[k];
+            bool textured = m.kind == RT_MAT_LAMBERTIAN || m.kind == RT_MAT_DIFFUSE_LIGHT || m.kind == RT_MAT_ISOTROPIC;
+            if (m.kind < RT_MAT_LAMBERTIAN || m.kind > RT_MAT_ISOTROPIC) return fail(RT_ERR_INVALID, "unknown material kind");
+            if (textured) {
+                if (m.texture < 0 || m.texture >= d->n_textures) return fail(RT_ERR_INVALID, "material texture index out of range");
+                const RtTexture& t = d->textures[m.texture];
+                if (t.kind == RT_TEX_SOLID) {  // fold constant colours into the material record
+                    dm.tex = -1;
+                    for (int k = 0; k < 3; ++k) dm.albedo[k] = (float)t.color[k];
+                }
+            } else {
+                dm.tex = -1;
+            }
+            out.mats.push_back(dm);
+        }
+        for (int i = 0; i < d->n_textures; ++i) {
+            const RtTexture& t = d->textures[i];
+            DTexture dt{};
+            dt.kind = t.kind, dt.a = t.a, dt.b = t.b, dt.scale = (float)t.scale;
+            for (int k = 0; k < 3; ++k) dt.color[k] = (float)t.color[k];
+            if (t.kind == RT_TEX_CHECKER) {
+                // Checker<Odd,Even> nests by type in the reference; the device keeps one level (solid or any
+                // non-checker texture on each side), which covers every shipped world.
+                if (t.a < 0 || t.a >= d->n_textures || t.b < 0 || t.b >= d->n_textures) return fail(RT_ERR_INVALID, "checker child out of range");
+                if (d->textures[t.a].kind == RT_TEX_CHECKER || d->textures[t.b].kind == RT_TEX_CHECKER)
+                    return fail(RT_ERR_UNSUPPORTED, "nested checker textures");
+            } else if (t.kind == RT_TEX_NOISE) {
+                if (t.a < 0 || t.a >= d->n_perlins) return fail(RT_ERR_INVALID, "noise texture: perlin table out of range");
+            } else if (t.kind == RT_TEX_IMAGE) {
+                if (t.a < 0 || t.a >= d->n_images) return fail(RT_ERR_INVALID, "image texture: image out of range");
+            } else if (t.kind != RT_TEX_SOLID) {
+                return fail(RT_ERR_INVALID, "unknown texture kind");
+            }
+            out.texs.push_back(dt);
+        }
+        for (int i = 0; i < d->n_perlins; ++i) {
+            const RtPerlin& p = d->perlins[i];
+            for (int k = 0; k < RTB_PERLIN_POINTS; ++k) {
+                for (int c = 0; c < 3; ++c) out.perlin_vec.push_back((float)p.ranvec[k][c]);
+                out.perlin_vec.push_back(0.0f);
+            }
+            const int32_t* perms[3] = {p.perm_x, p.perm_y, p.perm_z};
+            for (const int32_t* perm : perms)
+                for (int k = 0; k < RTB_PERLIN_POINTS; ++k) {
+                    if (perm[k] < 0 || perm[k] >= RTB_PERLIN_POINTS) return fail(RT_ERR_INVALID, "perlin permutation entry out of range");
+                    out.perlin_perm.push_back((unsigned short)perm[k]);
+                }
+        }
+        for (int i = 0; i < d->n_images; ++i) {
+            const RtImage& im = d->images[i];
+            if (im.width <= 0 || im.height <= 0 || !im.rgb) return fail(RT_ERR_INVALID, "image without pixels");
+            FlatScene::Image fi;
+            fi.width = im.width, fi.height = im.height;
+            fi.rgba.resize((size_t)4 * im.width * im.height);
+            for (size_t px = 0; px < (size_t)im.width * im.height; ++px) {
+                fi.rgba[4 * px] = im.rgb[3 * px], fi.rgba[4 * px + 1] = im.rgb[3 * px + 1], fi.rgba[4 * px + 2] = im.rgb[3 * px + 2];
+                fi.rgba[4 * px + 3] = 255;
+            }
+            out.images.push_back(std::move(fi));
+        }
+        out.bg_kind = d->background_kind;
+        for (int k = 0; k < 3; ++k) out.bg_top[k] = (float)d->background_top[k], out.bg_bottom[k] = (float)d->background_bottom[k];
+        return true;
+    }
+};
+
+}  // namespace
+
+int flatten_scene(const RtSceneDesc* desc, int32_t root, bool build_bvh, FlatScene& out, std::string& err) {
+    if (!desc || desc->n_nodes <= 0 || !desc->nodes) {
+        err = "empty scene description";
+        return RT_ERR_INVALID;
+    }
+    if (desc->n_children > 0 && !desc->children) {
+        err = "children array missing";
+        return RT_ERR_INVALID;
+    }
+    Flattener f(desc, out, err);
+    if (!f.tables()) return f.status;
+    std::vector<Wrapper> chain;
+    f.walk(root, chain, 0);
+    if (f.status != RT_OK) return f.status;
+    if (build_bvh) f.build_bvh();
+    return f.status;
+}
+
+void make_camera(const RtCamera& in, DCamera& out) {
+    // Camera::new, camera.rs:15-38, all in f64 like the reference; only the result is narrowed
+    auto sub = [](const double a[3], const double b[3], double r[3]) { for (int i = 0; i < 3; ++i) r[i] = a[i] - b[i]; };
+    auto unit = [](double v[3]) {
+        double l = std::sqrt(v[0] * v[0] + v[1] * v[1] + v[2] * v[2]);
+        for (int i = 0; i < 3; ++i) v[i] /= l;
+    };
+    auto cross = [](const double a[3], const double b[3], double r[3]) {
+        r[0] = a[1] * b[2] - a[2] * b[1], r[1] = a[2] * b[0] - a[0] * b[2], r[2] = a[0] * b[1] - a[1] * b[0];
+    };
+    double theta = in.vfov_deg * kPi / 180.0;
+    double h = std::tan(theta / 2.0);
+    double vh = 2.0 * h, vw = in.aspect_ratio * vh;
+    double w[3], u[3], v[3];
+    sub(in.lookfrom, in.lookat, w);
+    unit(w);
+    cross(in.vup, w, u);
+    unit(u);
+    cross(w, u, v);
+    for (int i = 0; i < 3; ++i) {
+        double hor = in.focus_dist * vw * u[i], ver = in.focus_dist * vh * v[i];
+        out.origin[i] = (float)in.lookfrom[i];
+        out.horizontal[i] = (float)hor, out.vertical[i] = (float)ver;
+        // stored relative to the origin: get_ray only ever uses lower_left_corner - origin (camera.rs:46)
+        double llc = in.lookfrom[i] - hor / 2.0 - ver / 2.0 - in.focus_dist * w[i];
+        out.lower_left[i] = (float)(llc - in.lookfrom[i]);
+        out.u[i] = (float)u[i], out.v[i] = (float)v[i];
+    }
+    out.lens_radius = (float)(in.aperture / 2.0);
+}
+
+}  // namespace rtb

@@ -1,0 +1,40 @@
+// Host-side flattening of a scene description into the device layout of rt_types.h.
+#pragma once
+#include <string>
+#include <vector>
+
+#include "../../include/rt_b200.h"
+#include "rt_types.h"
+
+namespace rtb {
+
+struct FlatScene {
+    std::vector<DNode> nodes;       // BVH over the surface primitives, root = 0
+    std::vector<DPrim> prims;       // in BVH leaf order
+    std::vector<int32_t> prim_node; // description node of each primitive
+    std::vector<DBigSphere> big;
+    std::vector<DInstance> inst;
+    std::vector<DMaterial> mats;    // same indexing as the description
+    std::vector<DTexture> texs;     // same indexing as the description
+    std::vector<DMedium> media;
+    std::vector<float> perlin_vec;           // n x 1024 x 4
+    std::vector<unsigned short> perlin_perm; // n x 3 x 1024
+    struct Image {
+        int32_t width, height;
+        std::vector<uint8_t> rgba;  // width*height*4, row 0 = top of the file
+    };
+    std::vector<Image> images;
+    int32_t bg_kind = 0;
+    float bg_top[3] = {0, 0, 0}, bg_bottom[3] = {0, 0, 0};
+    int32_t bvh_depth = 0;
+};
+
+// Flatten the subtree rooted at `root` (normally desc->root).  With build_bvh = false the primitives are
+// left in emission order and `nodes` stays empty (used by the brute-force test entry point).
+// Returns RT_OK or an RT_ERR_* code with `err` filled in.
+int flatten_scene(const RtSceneDesc* desc, int32_t root, bool build_bvh, FlatScene& out, std::string& err);
+
+// Camera::new (camera.rs:15-38) evaluated in f64, narrowed to the device record.
+void make_camera(const RtCamera& in, DCamera& out);
+
+}  // namespace rtb

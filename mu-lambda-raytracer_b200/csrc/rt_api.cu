@@ -1,0 +1,532 @@
+// CUDA side of librt_b200: kernels + the extern "C" entry points of include/rt_b200.h that touch the device.
+//
+// The boundary replaced here is Renderer::new_with_rng + Renderer::render (src/raytrace.rs:151-186) as called by
+// do_tracing (src/main.rs:147-157).  There is NO CPU fallback: without a CUDA device every entry point returns
+// RT_ERR_NO_DEVICE.
+#include <cuda_runtime.h>
+
+#include <algorithm>
+#include <cstdio>
+#include <cstring>
+#include <string>
+#include <vector>
+
+#include "flatten.h"
+#include "internal.h"
+#include "rt_device.cuh"
+
+using namespace rtb;
+
+// ============================================================================ kernels
+
+// Megakernel: one thread integrates `samples_per_item` consecutive samples of one pixel (regenerating paths in
+// place), a warp covers an 8x4 pixel tile, and the per-thread sum is added to the accumulation buffer with three
+// float reductions.  rays_out counts path segments (warp-aggregated).
+__global__ void __launch_bounds__(128) render_items_kernel(DSceneView S, DCamera cam, DRenderParams P, long long n_items, int total_samples,
+                                                           float* __restrict__ accum, unsigned long long* __restrict__ rays_out) {
+    long long item = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    uint32_t n_rays = 0;
+    int px, py, chunk;
+    if (item < n_items && item_to_pixel(P, item, px, py, chunk)) {
+        int first = chunk * P.samples_per_item;
+        int count = min(P.samples_per_item, total_samples - first);
+        float sum[3];
+        integrate_item(S, cam, P, px, py, P.sample_begin + first, count, sum, n_rays);
+        float* dst = accum + 3 * ((size_t)py * P.width + px);
+        atomicAdd(dst + 0, sum[0]);
+        atomicAdd(dst + 1, sum[1]);
+        atomicAdd(dst + 2, sum[2]);
+    }
+    // one counter update per warp
+    for (int off = 16; off > 0; off >>= 1) n_rays += __shfl_down_sync(0xffffffffu, n_rays, off);
+    if ((threadIdx.x & 31) == 0 && n_rays) atomicAdd(rays_out, (unsigned long long)n_rays);
+}
+
+// to_rgb (raytrace.rs:59-68): gamma 2, clamp, x255.999, truncate.  Done in f64 so that, given the same sums, the
+// bytes are the reference's.
+__global__ void tonemap_kernel(const float* __restrict__ accum, int32_t* __restrict__ rgb, int n_values, double scale) {
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n_values) return;
+    double x = sqrt((double)accum[i] * scale);
+    x = x < 0.0 ? 0.0 : (x > 0.99999999 ? 0.99999999 : x);  // f64::clamp keeps NaN; `as i32` maps NaN to 0
+    double y = 255.999 * x;
+    rgb[i] = (y != y) ? 0 : (int32_t)y;
+}
+
+__global__ void intersect_kernel(DSceneView S, int mode, const float* __restrict__ rays, long long n, RtHit* __restrict__ out) {
+    long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    float q[8];
+    for (int k = 0; k < 8; ++k) q[k] = rays[8 * i + k];
+    RtHit h;
+    intersect_query(S, mode, q, h);
+    out[i] = h;
+}
+
+__global__ void texture_kernel(DSceneView S, int tex, const float* __restrict__ uvp, long long n, float* __restrict__ rgb) {
+    long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const float* q = uvp + 5 * i;
+    V3 c = texture_value(S, tex, q[0], q[1], v3(q[2], q[3], q[4]));
+    rgb[3 * i] = c.x, rgb[3 * i + 1] = c.y, rgb[3 * i + 2] = c.z;
+}
+
+__global__ void camera_kernel(DCamera cam, DRenderParams P, const int32_t* __restrict__ pixel, const int32_t* __restrict__ sample, long long n,
+                              float* __restrict__ rays, float* __restrict__ us) {
+    long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    float r6[6], u4[4];
+    camera_query(cam, P, pixel[i], sample[i], r6, u4);
+    for (int k = 0; k < 6; ++k) rays[6 * i + k] = r6[k];
+    for (int k = 0; k < 4; ++k) us[4 * i + k] = u4[k];
+}
+
+// ============================================================================ host-side scene object
+
+namespace {
+
+#define CU_TRY(expr)                                                                                         \
+    do {                                                                                                     \
+        cudaError_t e_ = (expr);                                                                             \
+        if (e_ != cudaSuccess) return set_error(RT_ERR_CUDA, "%s failed: %s", #expr, cudaGetErrorString(e_)); \
+    } while (0)
+
+struct DeviceGuard {  // run on the scene's device, restore the caller's afterwards
+    int prev = -1;
+    explicit DeviceGuard(int dev) {
+        cudaGetDevice(&prev);
+        if (dev != prev) cudaSetDevice(dev);
+    }
+    ~DeviceGuard() {
+        int cur = -1;
+        cudaGetDevice(&cur);
+        if (prev >= 0 && cur != prev) cudaSetDevice(prev);
+    }
+};
+
+template <class T>
+int upload(const std::vector<T>& v, T** out, std::vector<void*>& owned, int64_t& bytes) {
+    *out = nullptr;
+    size_t n = std::max<size_t>(v.size(), 1) * sizeof(T);  // never a null table
+    void* p = nullptr;
+    CU_TRY(cudaMalloc(&p, n));
+    owned.push_back(p);
+    if (!v.empty()) CU_TRY(cudaMemcpy(p, v.data(), v.size() * sizeof(T), cudaMemcpyHostToDevice));
+    *out = (T*)p;
+    bytes += (int64_t)n;
+    return RT_OK;
+}
+
+}  // namespace
+
+struct RtScene {
+    int device = 0;
+    DSceneView view{};
+    FlatScene flat;  // host copy (info + hit -> description node mapping)
+    std::vector<void*> owned;
+    std::vector<cudaArray_t> arrays;
+    std::vector<cudaTextureObject_t> textures;
+    int64_t device_bytes = 0;
+    rtb::OwnedDesc* desc = nullptr;  // deep copy of the description (sub-tree queries of rt_intersect_batch)
+    // scratch of rt_render (host-buffer entry point), grown on demand
+    float* d_accum = nullptr;
+    int32_t* d_rgb = nullptr;
+    size_t scratch_values = 0;
+    unsigned long long* d_rays = nullptr;
+    cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+};
+
+namespace {
+
+int have_device() {
+    int n = 0;
+    cudaError_t e = cudaGetDeviceCount(&n);
+    if (e != cudaSuccess || n <= 0) {
+        cudaGetLastError();
+        return set_error(RT_ERR_NO_DEVICE, "no usable CUDA device (%s); librt_b200 has no CPU path", e == cudaSuccess ? "device count is 0" : cudaGetErrorString(e));
+    }
+    return RT_OK;
+}
+
+int upload_scene(RtScene* s) {
+    FlatScene& f = s->flat;
+    DSceneView& v = s->view;
+    DNode* nodes;
+    DPrim* prims;
+    DBigSphere* big;
+    DInstance* inst;
+    DMaterial* mats;
+    DTexture* texs;
+    DMedium* media;
+    float* pvec;
+    unsigned short* pperm;
+    int rc;
+    if ((rc = upload(f.nodes, &nodes, s->owned, s->device_bytes))) return rc;
+    if ((rc = upload(f.prims, &prims, s->owned, s->device_bytes))) return rc;
+    if ((rc = upload(f.big, &big, s->owned, s->device_bytes))) return rc;
+    if ((rc = upload(f.inst, &inst, s->owned, s->device_bytes))) return rc;
+    if ((rc = upload(f.mats, &mats, s->owned, s->device_bytes))) return rc;
+    if ((rc = upload(f.texs, &texs, s->owned, s->device_bytes))) return rc;
+    if ((rc = upload(f.media, &media, s->owned, s->device_bytes))) return rc;
+    if ((rc = upload(f.perlin_vec, &pvec, s->owned, s->device_bytes))) return rc;
+    if ((rc = upload(f.perlin_perm, &pperm, s->owned, s->device_bytes))) return rc;
+    // image textures -> CUDA texture objects (RGBA8, point sampling, clamp, texel coordinates)
+    std::vector<DImage> images;
+    for (auto& im : f.images) {
+        cudaChannelFormatDesc cd = cudaCreateChannelDesc<uchar4>();
+        cudaArray_t arr = nullptr;
+        CU_TRY(cudaMallocArray(&arr, &cd, im.width, im.height));
+        s->arrays.push_back(arr);
+        CU_TRY(cudaMemcpy2DToArray(arr, 0, 0, im.rgba.data(), (size_t)im.width * 4, (size_t)im.width * 4, im.height, cudaMemcpyHostToDevice));
+        cudaResourceDesc rd{};
+        rd.resType = cudaResourceTypeArray;
+        rd.res.array.array = arr;
+        cudaTextureDesc td{};
+        td.addressMode[0] = td.addressMode[1] = cudaAddressModeClamp;
+        td.filterMode = cudaFilterModePoint;
+        td.readMode = cudaReadModeElementType;
+        td.normalizedCoords = 0;
+        cudaTextureObject_t tex = 0;
+        CU_TRY(cudaCreateTextureObject(&tex, &rd, &td, nullptr));
+        s->textures.push_back(tex);
+        images.push_back(DImage{(unsigned long long)tex, im.width, im.height});
+        s->device_bytes += (int64_t)im.width * im.height * 4;
+    }
+    DImage* dimages;
+    if ((rc = upload(images, &dimages, s->owned, s->device_bytes))) return rc;
+    v.nodes = nodes, v.prims = prims, v.big = big, v.inst = inst, v.mats = mats, v.texs = texs, v.media = media;
+    v.perlin_vec = pvec, v.perlin_perm = pperm, v.images = dimages;
+    v.n_nodes = (int)f.nodes.size(), v.n_prims = (int)f.prims.size(), v.n_media = (int)f.media.size();
+    v.n_perlin = (int)(f.perlin_vec.size() / (4 * RTB_PERLIN_POINTS));
+    v.bg_kind = f.bg_kind;
+    for (int k = 0; k < 3; ++k) v.bg_top[k] = f.bg_top[k], v.bg_bottom[k] = f.bg_bottom[k];
+    return RT_OK;
+}
+
+void free_scene(RtScene* s) {
+    if (!s) return;
+    {
+        DeviceGuard g(s->device);
+        for (auto t : s->textures) cudaDestroyTextureObject(t);
+        for (auto a : s->arrays) cudaFreeArray(a);
+        for (void* p : s->owned) cudaFree(p);
+        if (s->d_accum) cudaFree(s->d_accum);
+        if (s->d_rgb) cudaFree(s->d_rgb);
+        if (s->d_rays) cudaFree(s->d_rays);
+        if (s->ev0) cudaEventDestroy(s->ev0);
+        if (s->ev1) cudaEventDestroy(s->ev1);
+    }
+    if (s->desc) rtb::free_desc(s->desc);
+    delete s;
+}
+
+int create_scene(const RtSceneDesc* desc, int32_t root, bool build_bvh, int device, bool keep_desc, RtScene** out) {
+    RtScene* s = new RtScene();
+    std::string err;
+    int rc = flatten_scene(desc, root, build_bvh, s->flat, err);
+    if (rc != RT_OK) {
+        delete s;
+        return set_error(rc, "%s", err.c_str());
+    }
+    if (device < 0) cudaGetDevice(&device);
+    s->device = device;
+    DeviceGuard g(device);
+    rc = upload_scene(s);
+    if (rc == RT_OK && cudaMalloc(&s->d_rays, sizeof(unsigned long long)) != cudaSuccess) rc = set_error(RT_ERR_CUDA, "cudaMalloc failed");
+    if (rc == RT_OK && (cudaEventCreate(&s->ev0) != cudaSuccess || cudaEventCreate(&s->ev1) != cudaSuccess)) rc = set_error(RT_ERR_CUDA, "cudaEventCreate failed");
+    if (rc != RT_OK) {
+        free_scene(s);
+        return rc;
+    }
+    if (keep_desc) s->desc = rtb::clone_desc(desc);
+    *out = s;
+    return RT_OK;
+}
+
+int validate_render(const RtScene* scene, const RtCamera* cam, const RtParams* p) {
+    if (!scene || !cam || !p) return set_error(RT_ERR_INVALID, "render: null argument");
+    if (p->width < 2 || p->height < 2) return set_error(RT_ERR_INVALID, "render: image must be at least 2x2 (u = (i+U)/(W-1))");
+    if ((long long)p->width * p->height > (1ll << 31) / 3) return set_error(RT_ERR_INVALID, "render: image too large");
+    if (p->samples_per_pixel <= 0 || p->max_depth < 0) return set_error(RT_ERR_INVALID, "render: samples_per_pixel must be > 0 and max_depth >= 0");
+    if (p->sample_begin < 0 || p->sample_count < 0) return set_error(RT_ERR_INVALID, "render: negative sample range");
+    if (p->pipeline < RT_PIPELINE_AUTO || p->pipeline > RT_PIPELINE_WAVEFRONT) return set_error(RT_ERR_INVALID, "render: unknown pipeline");
+    return RT_OK;
+}
+
+DRenderParams device_params(const RtParams* p, int first_sample, int spi, int chunks) {
+    DRenderParams P{};
+    P.width = p->width, P.height = p->height, P.max_depth = p->max_depth;
+    P.sample_begin = first_sample, P.samples_per_item = spi, P.items_per_pixel = chunks;
+    P.tiles_x = (p->width + 7) / 8, P.tiles_y = (p->height + 3) / 4;
+    P.seed_lo = (uint32_t)p->seed, P.seed_hi = (uint32_t)(p->seed >> 32);
+    P.inv_wm1 = 1.0f / ((float)p->width - 1.0f), P.inv_hm1 = 1.0f / ((float)p->height - 1.0f);
+    return P;
+}
+
+// the megakernel pipeline: samples [begin, begin+count) of every pixel, added into d_accum
+int launch_megakernel(const RtScene* s, const DCamera& cam, const RtParams* p, int begin, int count, float* d_accum, cudaStream_t stream,
+                      RtProgressFn cb, void* user, int* launches) {
+    int spi = p->samples_per_item > 0 ? p->samples_per_item : 16;
+    spi = std::min(spi, count);
+    long long pixels_padded = (long long)((p->width + 7) / 8) * ((p->height + 3) / 4) * 32;
+    // bound one launch to ~2^28 camera paths so that progress can be reported and no launch runs for seconds
+    long long max_chunks = std::max<long long>(1, (1ll << 28) / (pixels_padded * spi));
+    int done = 0;
+    while (done < count) {
+        int chunks_left = (count - done + spi - 1) / spi;
+        int chunks = (int)std::min<long long>(chunks_left, max_chunks);
+        int samples = std::min(count - done, chunks * spi);
+        DRenderParams P = device_params(p, begin + done, spi, chunks);
+        long long n_items = pixels_padded * chunks;
+        unsigned blocks = (unsigned)((n_items + 127) / 128);
+        render_items_kernel<<<blocks, 128, 0, stream>>>(s->view, cam, P, n_items, samples, d_accum, s->d_rays);
+        CU_TRY(cudaGetLastError());
+        *launches += 1;
+        done += samples;
+        if (cb) {
+            CU_TRY(cudaStreamSynchronize(stream));
+            cb(done, count, user);
+        }
+    }
+    return RT_OK;
+}
+
+}  // namespace
+
+// ============================================================================ extern "C"
+
+extern "C" {
+
+int rt_device_count(void) {
+    int n = 0;
+    if (cudaGetDeviceCount(&n) != cudaSuccess) {
+        cudaGetLastError();
+        return 0;
+    }
+    return n;
+}
+
+int rt_scene_create(const RtSceneDesc* desc, int device, RtScene** out) {
+    if (!desc || !out) return set_error(RT_ERR_INVALID, "rt_scene_create: null argument");
+    *out = nullptr;
+    int rc = have_device();
+    if (rc != RT_OK) return rc;
+    if (device >= rt_device_count()) return set_error(RT_ERR_INVALID, "rt_scene_create: device %d does not exist", device);
+    return create_scene(desc, desc->root, true, device, true, out);
+}
+
+void rt_scene_destroy(RtScene* scene) { free_scene(scene); }
+
+int rt_scene_info(const RtScene* scene, int32_t* n_prims, int32_t* n_bvh_nodes, int32_t* n_media, int64_t* device_bytes) {
+    if (!scene) return set_error(RT_ERR_INVALID, "rt_scene_info: null scene");
+    if (n_prims) *n_prims = (int32_t)scene->flat.prims.size();
+    if (n_bvh_nodes) *n_bvh_nodes = (int32_t)scene->flat.nodes.size();
+    if (n_media) *n_media = (int32_t)scene->flat.media.size();
+    if (device_bytes) *device_bytes = scene->device_bytes;
+    return RT_OK;
+}
+
+int rt_render_accumulate_device(const RtScene* scene, const RtCamera* cam, const RtParams* params, float* d_accum_rgb, void* stream_, RtStats* stats) {
+    int rc = validate_render(scene, cam, params);
+    if (rc != RT_OK) return rc;
+    if (!d_accum_rgb) return set_error(RT_ERR_INVALID, "rt_render_accumulate_device: null accumulation buffer");
+    if (params->pipeline == RT_PIPELINE_WAVEFRONT) return set_error(RT_ERR_UNSUPPORTED, "wavefront pipeline is not built yet");
+    cudaStream_t stream = (cudaStream_t)stream_;
+    DeviceGuard g(scene->device);
+    int begin = params->sample_begin;
+    int count = params->sample_count > 0 ? params->sample_count : params->samples_per_pixel - begin;
+    if (count <= 0) return set_error(RT_ERR_INVALID, "render: empty sample range");
+    DCamera dc;
+    make_camera(*cam, dc);
+    int launches = 0;
+    if (stats) {
+        CU_TRY(cudaMemsetAsync(scene->d_rays, 0, sizeof(unsigned long long), stream));
+        CU_TRY(cudaEventRecord(scene->ev0, stream));
+    }
+    rc = launch_megakernel(scene, dc, params, begin, count, d_accum_rgb, stream, nullptr, nullptr, &launches);
+    if (rc != RT_OK) return rc;
+    if (stats) {
+        CU_TRY(cudaEventRecord(scene->ev1, stream));
+        CU_TRY(cudaEventSynchronize(scene->ev1));
+        float ms = 0;
+        CU_TRY(cudaEventElapsedTime(&ms, scene->ev0, scene->ev1));
+        unsigned long long rays = 0;
+        CU_TRY(cudaMemcpy(&rays, scene->d_rays, sizeof rays, cudaMemcpyDeviceToHost));
+        stats->paths = (uint64_t)params->width * params->height * count;
+        stats->rays = rays;
+        stats->device_ms = ms;
+        stats->kernel_launches = launches;
+        stats->pipeline_used = RT_PIPELINE_MEGAKERNEL;
+    }
+    return RT_OK;
+}
+
+int rt_tonemap_device(const float* d_accum_rgb, int32_t* d_rgb, int32_t n_pixels, int32_t samples_per_pixel, int device, void* stream_) {
+    if (!d_accum_rgb || !d_rgb || n_pixels <= 0 || samples_per_pixel <= 0) return set_error(RT_ERR_INVALID, "rt_tonemap_device: bad argument");
+    int rc = have_device();
+    if (rc != RT_OK) return rc;
+    if (device < 0) cudaGetDevice(&device);
+    DeviceGuard g(device);
+    int n = 3 * n_pixels;
+    tonemap_kernel<<<(n + 255) / 256, 256, 0, (cudaStream_t)stream_>>>(d_accum_rgb, d_rgb, n, 1.0 / (double)samples_per_pixel);
+    CU_TRY(cudaGetLastError());
+    return RT_OK;
+}
+
+int rt_render(const RtScene* scene_, const RtCamera* cam, const RtParams* params, float* accum_rgb, int32_t* rgb, RtProgressFn cb, void* user,
+              RtStats* stats) {
+    int rc = validate_render(scene_, cam, params);
+    if (rc != RT_OK) return rc;
+    if (params->pipeline == RT_PIPELINE_WAVEFRONT) return set_error(RT_ERR_UNSUPPORTED, "wavefront pipeline is not built yet");
+    RtScene* scene = const_cast<RtScene*>(scene_);  // scratch buffers are cached in the scene object
+    DeviceGuard g(scene->device);
+    size_t n_values = (size_t)3 * params->width * params->height;
+    if (scene->scratch_values < n_values) {
+        if (scene->d_accum) cudaFree(scene->d_accum);
+        if (scene->d_rgb) cudaFree(scene->d_rgb);
+        scene->d_accum = nullptr, scene->d_rgb = nullptr, scene->scratch_values = 0;
+        CU_TRY(cudaMalloc(&scene->d_accum, n_values * sizeof(float)));
+        CU_TRY(cudaMalloc(&scene->d_rgb, n_values * sizeof(int32_t)));
+        scene->scratch_values = n_values;
+    }
+    int begin = params->sample_begin;
+    int count = params->sample_count > 0 ? params->sample_count : params->samples_per_pixel - begin;
+    if (count <= 0) return set_error(RT_ERR_INVALID, "render: empty sample range");
+    DCamera dc;
+    make_camera(*cam, dc);
+    cudaStream_t stream = 0;
+    int launches = 0;
+    CU_TRY(cudaMemsetAsync(scene->d_rays, 0, sizeof(unsigned long long), stream));
+    CU_TRY(cudaEventRecord(scene->ev0, stream));
+    CU_TRY(cudaMemsetAsync(scene->d_accum, 0, n_values * sizeof(float), stream));
+    rc = launch_megakernel(scene, dc, params, begin, count, scene->d_accum, stream, cb, user, &launches);
+    if (rc != RT_OK) return rc;
+    tonemap_kernel<<<(unsigned)((n_values + 255) / 256), 256, 0, stream>>>(scene->d_accum, scene->d_rgb, (int)n_values, 1.0 / (double)params->samples_per_pixel);
+    CU_TRY(cudaGetLastError());
+    launches += 1;
+    CU_TRY(cudaEventRecord(scene->ev1, stream));
+    if (accum_rgb) CU_TRY(cudaMemcpyAsync(accum_rgb, scene->d_accum, n_values * sizeof(float), cudaMemcpyDeviceToHost, stream));
+    if (rgb) CU_TRY(cudaMemcpyAsync(rgb, scene->d_rgb, n_values * sizeof(int32_t), cudaMemcpyDeviceToHost, stream));
+    CU_TRY(cudaStreamSynchronize(stream));
+    if (stats) {
+        float ms = 0;
+        CU_TRY(cudaEventElapsedTime(&ms, scene->ev0, scene->ev1));
+        unsigned long long rays = 0;
+        CU_TRY(cudaMemcpy(&rays, scene->d_rays, sizeof rays, cudaMemcpyDeviceToHost));
+        stats->paths = (uint64_t)params->width * params->height * count;
+        stats->rays = rays;
+        stats->device_ms = ms;
+        stats->kernel_launches = launches;
+        stats->pipeline_used = RT_PIPELINE_MEGAKERNEL;
+    }
+    return RT_OK;
+}
+
+int rt_intersect_batch(const RtScene* scene, int32_t node, const float* rays, int64_t n, RtHit* out) {
+    if (!scene || !rays || !out || n < 0) return set_error(RT_ERR_INVALID, "rt_intersect_batch: bad argument");
+    if (n == 0) return RT_OK;
+    DeviceGuard g(scene->device);
+    const RtScene* target = scene;
+    RtScene* sub = nullptr;
+    int mode = QUERY_BVH;
+    std::vector<int32_t> node_of_prim;
+    if (node >= 0 && scene->desc && node != scene->desc->d.root) {
+        // a sub-tree: flatten it on its own (no outer transforms) and test it by brute force
+        if (node >= scene->desc->d.n_nodes) return set_error(RT_ERR_INVALID, "rt_intersect_batch: node %d out of range", node);
+        int rc = create_scene(&scene->desc->d, node, false, scene->device, false, &sub);
+        if (rc != RT_OK) return rc;
+        target = sub;
+        mode = scene->desc->d.nodes[node].kind == RT_NODE_MEDIUM ? QUERY_MEDIUM : QUERY_LINEAR;
+    }
+    float* d_rays = nullptr;
+    RtHit* d_out = nullptr;
+    int rc = RT_OK;
+    do {
+        if (cudaMalloc(&d_rays, (size_t)n * 8 * sizeof(float)) != cudaSuccess || cudaMalloc(&d_out, (size_t)n * sizeof(RtHit)) != cudaSuccess) {
+            rc = set_error(RT_ERR_CUDA, "rt_intersect_batch: cudaMalloc failed");
+            break;
+        }
+        if (cudaMemcpy(d_rays, rays, (size_t)n * 8 * sizeof(float), cudaMemcpyHostToDevice) != cudaSuccess) {
+            rc = set_error(RT_ERR_CUDA, "rt_intersect_batch: upload failed");
+            break;
+        }
+        intersect_kernel<<<(unsigned)((n + 127) / 128), 128>>>(target->view, mode, d_rays, n, d_out);
+        cudaError_t e = cudaDeviceSynchronize();
+        if (e != cudaSuccess) {
+            rc = set_error(RT_ERR_CUDA, "rt_intersect_batch: kernel failed: %s", cudaGetErrorString(e));
+            break;
+        }
+        if (cudaMemcpy(out, d_out, (size_t)n * sizeof(RtHit), cudaMemcpyDeviceToHost) != cudaSuccess) {
+            rc = set_error(RT_ERR_CUDA, "rt_intersect_batch: download failed");
+            break;
+        }
+        // report description node ids instead of device primitive indices
+        for (int64_t i = 0; i < n; ++i)
+            if (out[i].prim >= 0) out[i].prim = target->flat.prim_node[out[i].prim];
+    } while (0);
+    cudaFree(d_rays);
+    cudaFree(d_out);
+    if (sub) free_scene(sub);
+    return rc;
+}
+
+int rt_texture_value_batch(const RtScene* scene, int32_t texture, const float* uvp, int64_t n, float* out_rgb) {
+    if (!scene || !uvp || !out_rgb || n < 0) return set_error(RT_ERR_INVALID, "rt_texture_value_batch: bad argument");
+    if (texture < 0 || texture >= (int)scene->flat.texs.size()) return set_error(RT_ERR_INVALID, "rt_texture_value_batch: texture %d out of range", texture);
+    if (n == 0) return RT_OK;
+    DeviceGuard g(scene->device);
+    float *d_in = nullptr, *d_out = nullptr;
+    int rc = RT_OK;
+    do {
+        if (cudaMalloc(&d_in, (size_t)n * 5 * sizeof(float)) != cudaSuccess || cudaMalloc(&d_out, (size_t)n * 3 * sizeof(float)) != cudaSuccess) {
+            rc = set_error(RT_ERR_CUDA, "rt_texture_value_batch: cudaMalloc failed");
+            break;
+        }
+        cudaMemcpy(d_in, uvp, (size_t)n * 5 * sizeof(float), cudaMemcpyHostToDevice);
+        texture_kernel<<<(unsigned)((n + 127) / 128), 128>>>(scene->view, texture, d_in, n, d_out);
+        cudaError_t e = cudaDeviceSynchronize();
+        if (e != cudaSuccess) {
+            rc = set_error(RT_ERR_CUDA, "rt_texture_value_batch: kernel failed: %s", cudaGetErrorString(e));
+            break;
+        }
+        cudaMemcpy(out_rgb, d_out, (size_t)n * 3 * sizeof(float), cudaMemcpyDeviceToHost);
+    } while (0);
+    cudaFree(d_in);
+    cudaFree(d_out);
+    return rc;
+}
+
+int rt_generate_rays(const RtCamera* cam, const RtParams* params, const int32_t* pixel, const int32_t* sample, int64_t n, float* out_rays,
+                     float* out_sample) {
+    if (!cam || !params || !pixel || !sample || !out_rays || !out_sample || n < 0) return set_error(RT_ERR_INVALID, "rt_generate_rays: bad argument");
+    if (params->width < 2 || params->height < 2) return set_error(RT_ERR_INVALID, "rt_generate_rays: image must be at least 2x2");
+    int rc = have_device();
+    if (rc != RT_OK) return rc;
+    if (n == 0) return RT_OK;
+    DCamera dc;
+    make_camera(*cam, dc);
+    DRenderParams P = device_params(params, 0, 1, 1);
+    int32_t *d_px = nullptr, *d_s = nullptr;
+    float *d_r = nullptr, *d_u = nullptr;
+    do {
+        if (cudaMalloc(&d_px, (size_t)n * 4) != cudaSuccess || cudaMalloc(&d_s, (size_t)n * 4) != cudaSuccess ||
+            cudaMalloc(&d_r, (size_t)n * 24) != cudaSuccess || cudaMalloc(&d_u, (size_t)n * 16) != cudaSuccess) {
+            rc = set_error(RT_ERR_CUDA, "rt_generate_rays: cudaMalloc failed");
+            break;
+        }
+        cudaMemcpy(d_px, pixel, (size_t)n * 4, cudaMemcpyHostToDevice);
+        cudaMemcpy(d_s, sample, (size_t)n * 4, cudaMemcpyHostToDevice);
+        camera_kernel<<<(unsigned)((n + 127) / 128), 128>>>(dc, P, d_px, d_s, n, d_r, d_u);
+        cudaError_t e = cudaDeviceSynchronize();
+        if (e != cudaSuccess) {
+            rc = set_error(RT_ERR_CUDA, "rt_generate_rays: kernel failed: %s", cudaGetErrorString(e));
+            break;
+        }
+        cudaMemcpy(out_rays, d_r, (size_t)n * 24, cudaMemcpyDeviceToHost);
+        cudaMemcpy(out_sample, d_u, (size_t)n * 16, cudaMemcpyDeviceToHost);
+    } while (0);
+    cudaFree(d_px), cudaFree(d_s), cudaFree(d_r), cudaFree(d_u);
+    return rc;
+}
+
+}  // extern "C"

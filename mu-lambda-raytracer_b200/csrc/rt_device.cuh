@@ -1,0 +1,790 @@
+// Device-side path tracing: everything between "a (pixel, sample) index" and "a radiance sample".
+//
+// This is the B200 re-design of the reference's hot path:
+//   Camera::get_ray             src/camera.rs:40-48        -> generate_camera_ray
+//   Hittable::hit dispatch      src/hittable.rs:53-68,
+//                               src/bhv.rs:147-165         -> closest_hit (flat 32-byte-node BVH, short stack)
+//   Sphere / AARect / Block     src/shapes.rs:57-82,
+//                               src/aarects.rs:45-64       -> hit_sphere / hit_box (rects are flat boxes)
+//   Translate / Rotate          src/transforms.rs:31-42,
+//                               :127-142                   -> DInstance (composed rigid transform)
+//   ConstantMedium::hit         src/volumes.rs:25-65       -> sample_media
+//   Material::scatter / emit    src/materials.rs:25-127,
+//                               src/volumes.rs:77-83       -> shade_hit
+//   Texture::value              src/textures.rs:22-167,
+//                               src/image_texture.rs:16-28 -> texture_value
+//   trace_internal              src/raytrace.rs:79-101     -> the iterative loop in integrate_item
+// Arithmetic is f32 (f64 only for spheres with |r| >= 100, whose quadratic cancels catastrophically in f32);
+// random numbers are counter-based Philox4x32-10 keyed by (seed; pixel, sample, draw).
+//
+// The file also compiles as plain C++ (RTB_HOST_EMULATION) so that tests/ can run the very same functions on
+// the CPU against the oracle; that build is test infrastructure only and is never part of librt_b200.so.
+#pragma once
+#include <math.h>
+#include <stdint.h>
+
+#include "../../include/rt_b200.h"
+#include "rt_types.h"
+
+#if defined(__CUDACC__) && !defined(RTB_HOST_EMULATION)
+#define RTB_DEV __device__ __forceinline__
+#define RTB_DEV_NOINLINE __device__ __noinline__
+namespace rtb {
+RTB_DEV float4 ld4(const void* p) { return __ldg(reinterpret_cast<const float4*>(p)); }
+RTB_DEV uint32_t mulhi32(uint32_t a, uint32_t b) { return __umulhi(a, b); }
+RTB_DEV float u32_to_unit(uint32_t x) { return __uint2float_rz(x) * 2.3283064365386963e-10f; }
+RTB_DEV void sincos_2pi(float x, float* s, float* c) { sincospif(2.0f * x, s, c); }
+RTB_DEV float fast_cbrt(float x) { return __powf(x, 0.33333334f); }
+RTB_DEV float fast_log(float x) { return __logf(x); }
+RTB_DEV float as_float(uint32_t u) { return __uint_as_float(u); }
+RTB_DEV uint32_t as_uint(float f) { return __float_as_uint(f); }
+RTB_DEV void image_fetch(const DImage& im, int i, int j, float rgb[3]) {
+    uchar4 px = tex2D<uchar4>((cudaTextureObject_t)im.tex, (float)i + 0.5f, (float)j + 0.5f);
+    rgb[0] = (float)px.x / 255.0f, rgb[1] = (float)px.y / 255.0f, rgb[2] = (float)px.z / 255.0f;
+}
+}  // namespace rtb
+#else
+#include <string.h>
+#define RTB_DEV inline
+#define RTB_DEV_NOINLINE inline
+namespace rtb {
+struct float4 {
+    float x, y, z, w;
+};
+inline float4 ld4(const void* p) {
+    float4 v;
+    memcpy(&v, p, 16);
+    return v;
+}
+inline uint32_t mulhi32(uint32_t a, uint32_t b) { return (uint32_t)(((uint64_t)a * b) >> 32); }
+inline float u32_to_unit(uint32_t x) {  // == __uint2float_rz(x) * 2^-32: keep the 24 leading significant bits
+    int drop = x ? 8 - __builtin_clz(x) : 0;
+    if (drop > 0) x = (x >> drop) << drop;
+    return (float)x * 2.3283064365386963e-10f;
+}
+inline void sincos_2pi(float x, float* s, float* c) {
+    *s = sinf(6.283185307179586f * x), *c = cosf(6.283185307179586f * x);
+}
+inline float fast_cbrt(float x) { return cbrtf(x); }
+inline float fast_log(float x) { return logf(x); }
+inline float as_float(uint32_t u) {
+    float f;
+    memcpy(&f, &u, 4);
+    return f;
+}
+inline uint32_t as_uint(float f) {
+    uint32_t u;
+    memcpy(&u, &f, 4);
+    return u;
+}
+inline void image_fetch(const DImage& im, int i, int j, float rgb[3]) {
+    const uint8_t* px = (const uint8_t*)(uintptr_t)im.tex + 4 * ((size_t)j * im.width + i);
+    rgb[0] = (float)px[0] / 255.0f, rgb[1] = (float)px[1] / 255.0f, rgb[2] = (float)px[2] / 255.0f;
+}
+}  // namespace rtb
+#endif
+
+namespace rtb {
+
+#define RTB_INF as_float(0x7f800000u)
+#define RTB_T_MIN 0.001f  // raytrace.rs:90, in units of the (unnormalised) direction
+
+// ------------------------------------------------------------------ small vector type
+struct V3 {
+    float x, y, z;
+};
+RTB_DEV V3 v3(float x, float y, float z) { return V3{x, y, z}; }
+RTB_DEV V3 operator+(V3 a, V3 b) { return V3{a.x + b.x, a.y + b.y, a.z + b.z}; }
+RTB_DEV V3 operator-(V3 a, V3 b) { return V3{a.x - b.x, a.y - b.y, a.z - b.z}; }
+RTB_DEV V3 operator-(V3 a) { return V3{-a.x, -a.y, -a.z}; }
+RTB_DEV V3 operator*(V3 a, V3 b) { return V3{a.x * b.x, a.y * b.y, a.z * b.z}; }
+RTB_DEV V3 operator*(float s, V3 a) { return V3{a.x * s, a.y * s, a.z * s}; }
+RTB_DEV V3 operator*(V3 a, float s) { return V3{a.x * s, a.y * s, a.z * s}; }
+RTB_DEV float dot(V3 a, V3 b) { return a.x * b.x + a.y * b.y + a.z * b.z; }
+RTB_DEV float comp(V3 a, int k) { return k == 0 ? a.x : (k == 1 ? a.y : a.z); }
+RTB_DEV V3 normalize(V3 a) {
+    float inv = 1.0f / sqrtf(dot(a, a));
+    return a * inv;
+}
+RTB_DEV V3 mul33(const float* m, V3 v) {  // row-major 3x3 times vector
+    return V3{m[0] * v.x + m[1] * v.y + m[2] * v.z, m[3] * v.x + m[4] * v.y + m[5] * v.z, m[6] * v.x + m[7] * v.y + m[8] * v.z};
+}
+RTB_DEV V3 mul33t(const float* m, V3 v) {  // transpose(m) times vector
+    return V3{m[0] * v.x + m[3] * v.y + m[6] * v.z, m[1] * v.x + m[4] * v.y + m[7] * v.z, m[2] * v.x + m[5] * v.y + m[8] * v.z};
+}
+
+struct Ray {
+    V3 o, d;
+};
+
+// ------------------------------------------------------------------ Philox4x32-10 (Salmon et al., SC'11)
+RTB_DEV void philox4x32_10(uint32_t c0, uint32_t c1, uint32_t c2, uint32_t c3, uint32_t k0, uint32_t k1, uint32_t out[4]) {
+    const uint32_t M0 = 0xD2511F53u, M1 = 0xCD9E8D57u, W0 = 0x9E3779B9u, W1 = 0xBB67AE85u;
+#pragma unroll
+    for (int round = 0; round < 10; ++round) {
+        uint32_t hi0 = mulhi32(M0, c0), lo0 = M0 * c0;
+        uint32_t hi1 = mulhi32(M1, c2), lo1 = M1 * c2;
+        uint32_t n0 = hi1 ^ c1 ^ k0, n2 = hi0 ^ c3 ^ k1;
+        c0 = n0, c1 = lo1, c2 = n2, c3 = lo0;
+        k0 += W0, k1 += W1;
+    }
+    out[0] = c0, out[1] = c1, out[2] = c2, out[3] = c3;
+}
+
+// one stream per camera path: counter = (pixel, sample, draw, tag), key = seed
+struct PathRng {
+    uint32_t pixel, sample, draw, k0, k1;
+};
+RTB_DEV void rng_next4(PathRng& g, float u[4]) {
+    uint32_t r[4];
+    philox4x32_10(g.pixel, g.sample, g.draw, 0x52544232u, g.k0, g.k1, r);
+    g.draw += 1;
+    u[0] = u32_to_unit(r[0]), u[1] = u32_to_unit(r[1]), u[2] = u32_to_unit(r[2]), u[3] = u32_to_unit(r[3]);
+}
+
+// Uniform point inside the unit ball, drawn directly instead of by the rejection loop of
+// Vec3::random_in_unit_sphere (vec.rs:23-30): same distribution, fixed cost.
+RTB_DEV V3 sample_unit_ball(float u0, float u1, float u2) {
+    float z = 1.0f - 2.0f * u0;
+    float rxy = sqrtf(fmaxf(0.0f, 1.0f - z * z));
+    float s, c;
+    sincos_2pi(u1, &s, &c);
+    float r = fast_cbrt(u2);
+    return V3{r * rxy * c, r * rxy * s, r * z};
+}
+
+// ------------------------------------------------------------------ camera (camera.rs:40-48, raytrace.rs:191-192)
+RTB_DEV Ray generate_camera_ray(const DCamera& cam, const DRenderParams& P, int px, int py, const float u[4]) {
+    float s = ((float)px + u[0]) * P.inv_wm1;
+    float t = ((float)py + u[1]) * P.inv_hm1;
+    V3 off = v3(0.f, 0.f, 0.f);
+    if (cam.lens_radius > 0.0f) {  // random_in_unit_disk (vec.rs:45-52) without the rejection loop
+        float r = cam.lens_radius * sqrtf(u[2]);
+        float sn, cs;
+        sincos_2pi(u[3], &sn, &cs);
+        float dx = r * cs, dy = r * sn;
+        off = v3(cam.u[0] * dx + cam.v[0] * dy, cam.u[1] * dx + cam.v[1] * dy, cam.u[2] * dx + cam.v[2] * dy);
+    }
+    Ray r;
+    r.o = v3(cam.origin[0], cam.origin[1], cam.origin[2]) + off;
+    r.d = v3(cam.lower_left[0] + s * cam.horizontal[0] + t * cam.vertical[0], cam.lower_left[1] + s * cam.horizontal[1] + t * cam.vertical[1],
+             cam.lower_left[2] + s * cam.horizontal[2] + t * cam.vertical[2]) -
+          off;
+    return r;
+}
+
+// ------------------------------------------------------------------ primitives
+struct PrimRec {  // a DPrim in registers
+    float v0, v1, v2, v3, v4, v5;
+    uint32_t meta;
+    int32_t mat;
+};
+RTB_DEV PrimRec load_prim(const DPrim* p) {
+    float4 a = ld4(p), b = ld4(reinterpret_cast<const char*>(p) + 16);
+    PrimRec r;
+    r.v0 = a.x, r.v1 = a.y, r.v2 = a.z, r.v3 = a.w, r.v4 = b.x, r.v5 = b.y;
+    r.meta = as_uint(b.z), r.mat = (int32_t)as_uint(b.w);
+    return r;
+}
+RTB_DEV int prim_instance(const PrimRec& p) { return (int)((p.meta >> PRIM_INST_SHIFT) & PRIM_INST_MASK); }
+
+// Sphere::hit (shapes.rs:57-82).  `from_surface`: the ray starts on this very sphere, so one root is
+// analytically zero (the reference rejects it through t_min) and the other is -2*half_b/a.
+RTB_DEV bool hit_sphere(const DSceneView& S, const PrimRec& p, const Ray& r, float tmin, float tmax, bool from_surface, float& t_out) {
+    float t0, t1;
+    if (p.meta & PRIM_BIG) {
+        const DBigSphere& b = S.big[as_uint(p.v4)];
+        double ocx = (double)r.o.x - b.c[0], ocy = (double)r.o.y - b.c[1], ocz = (double)r.o.z - b.c[2];
+        double dx = r.d.x, dy = r.d.y, dz = r.d.z;
+        double a = dx * dx + dy * dy + dz * dz;
+        double hb = ocx * dx + ocy * dy + ocz * dz;
+        if (from_surface) {
+            t0 = t1 = (float)(-2.0 * hb / a);
+        } else {
+            double c = ocx * ocx + ocy * ocy + ocz * ocz - b.r * b.r;
+            double disc = hb * hb - a * c;
+            if (disc < 0.0) return false;
+            double sq = sqrt(disc);
+            t0 = (float)((-hb - sq) / a), t1 = (float)((-hb + sq) / a);
+        }
+    } else {
+        V3 oc = r.o - v3(p.v0, p.v1, p.v2);
+        float a = dot(r.d, r.d);
+        float hb = dot(oc, r.d);
+        float inv_a = 1.0f / a;
+        if (from_surface) {
+            t0 = t1 = -2.0f * hb * inv_a;
+        } else {
+            // discriminant from the perpendicular offset |oc - (hb/a) d|^2: no cancellation for distant origins
+            V3 l = oc - (hb * inv_a) * r.d;
+            float disc_a = p.v3 * p.v3 - dot(l, l);
+            if (disc_a < 0.0f) return false;
+            float sq = sqrtf(a * disc_a);
+            float q = -(hb + copysignf(sq, hb));
+            float c = dot(oc, oc) - p.v3 * p.v3;
+            float ta = q * inv_a, tb = c / q;
+            t0 = fminf(ta, tb), t1 = fmaxf(ta, tb);
+        }
+    }
+    if (t0 >= tmin && t0 <= tmax) {
+        t_out = t0;
+        return true;
+    }
+    if (t1 >= tmin && t1 <= tmax) {
+        t_out = t1;
+        return true;
+    }
+    return false;
+}
+
+// both crossings of a sphere boundary over (-inf, +inf): what ConstantMedium asks of its boundary
+RTB_DEV bool sphere_interval(const DSceneView& S, const PrimRec& p, const Ray& r, float& t0, float& t1) {
+    if (p.meta & PRIM_BIG) {
+        const DBigSphere& b = S.big[as_uint(p.v4)];
+        double ocx = (double)r.o.x - b.c[0], ocy = (double)r.o.y - b.c[1], ocz = (double)r.o.z - b.c[2];
+        double dx = r.d.x, dy = r.d.y, dz = r.d.z;
+        double a = dx * dx + dy * dy + dz * dz;
+        double hb = ocx * dx + ocy * dy + ocz * dz;
+        double c = ocx * ocx + ocy * ocy + ocz * ocz - b.r * b.r;
+        double disc = hb * hb - a * c;
+        if (disc < 0.0) return false;
+        double sq = sqrt(disc);
+        t0 = (float)((-hb - sq) / a), t1 = (float)((-hb + sq) / a);
+        return true;
+    }
+    V3 oc = r.o - v3(p.v0, p.v1, p.v2);
+    float a = dot(r.d, r.d), hb = dot(oc, r.d), inv_a = 1.0f / a;
+    V3 l = oc - (hb * inv_a) * r.d;
+    float disc_a = p.v3 * p.v3 - dot(l, l);
+    if (disc_a < 0.0f) return false;
+    float sq = sqrtf(a * disc_a);
+    float q = -(hb + copysignf(sq, hb));
+    float c = dot(oc, oc) - p.v3 * p.v3;
+    float ta = q * inv_a, tb = c / q;
+    t0 = fminf(ta, tb), t1 = fmaxf(ta, tb);
+    return t0 == t0 && t1 == t1;
+}
+
+RTB_DEV Ray to_object_space(const DSceneView& S, int inst, const Ray& r) {
+    if (inst == 0) return r;
+    const DInstance& I = S.inst[inst - 1];
+    Ray o;
+    o.o = mul33t(I.rot, r.o - v3(I.trans[0], I.trans[1], I.trans[2]));
+    o.d = mul33t(I.rot, r.d);
+    return o;
+}
+
+// slab crossings of an object-space box; `origin_face` (axis | side << 2, or -1) pins the plane the ray
+// starts on to t = 0 exactly, which is what f64 gives the reference for a ray leaving that face.
+RTB_DEV bool box_slabs(const PrimRec& p, const Ray& r, int origin_face, float& t_enter, float& t_exit, int& face_enter, int& face_exit) {
+    float lo[3] = {p.v0, p.v1, p.v2}, hi[3] = {p.v3, p.v4, p.v5};
+    float o[3] = {r.o.x, r.o.y, r.o.z}, d[3] = {r.d.x, r.d.y, r.d.z};
+    t_enter = -RTB_INF, t_exit = RTB_INF;
+    face_enter = 0, face_exit = 0;
+#pragma unroll
+    for (int k = 0; k < 3; ++k) {
+        float inv = 1.0f / d[k];
+        float a = lo[k] - o[k], b = hi[k] - o[k];
+        if (origin_face >= 0 && (origin_face & 3) == k) {
+            if (origin_face >> 2) b = 0.0f;
+            else a = 0.0f;
+            if (lo[k] == hi[k]) a = b = 0.0f;  // a rect: both "sides" are the one plane
+        }
+        float ta = a * inv, tb = b * inv;
+        float tn = fminf(ta, tb), tf = fmaxf(ta, tb);  // fminf/fmaxf drop the NaN of 0 * inf
+        bool neg = d[k] < 0.0f;
+        if (tn > t_enter) t_enter = tn, face_enter = k | ((neg ? 1 : 0) << 2);
+        if (tf < t_exit) t_exit = tf, face_exit = k | ((neg ? 0 : 1) << 2);
+    }
+    return t_enter <= t_exit;
+}
+
+// AARect::hit / Block::hit (aarects.rs:45-64, shapes.rs:188-191): closest side with t in [tmin, tmax]
+RTB_DEV bool hit_box(const DSceneView& S, const PrimRec& p, const Ray& r_world, float tmin, float tmax, int origin_face, float& t_out, int& face_out) {
+    Ray r = to_object_space(S, prim_instance(p), r_world);
+    float te, tx;
+    int fe, fx;
+    if (!box_slabs(p, r, origin_face, te, tx, fe, fx)) return false;
+    int rect = (int)((p.meta >> PRIM_RECT_SHIFT) & PRIM_RECT_MASK);
+    if (rect) {  // a flat box: both crossings are the plane; report the plane's own axis
+        int k = rect - 1;
+        float dk = comp(r.d, k);
+        fe = fx = k | ((dk < 0.0f ? 1 : 0) << 2);
+    }
+    if (te >= tmin && te <= tmax) {
+        t_out = te, face_out = fe;
+        return true;
+    }
+    if (tx >= tmin && tx <= tmax) {
+        t_out = tx, face_out = fx;
+        return true;
+    }
+    return false;
+}
+
+RTB_DEV bool hit_prim(const DSceneView& S, const PrimRec& p, const Ray& r, float tmin, float tmax, bool is_origin, int origin_face, float& t, int& face) {
+    if ((p.meta & PRIM_KIND_MASK) == PRIM_SPHERE) {
+        face = 0;
+        return hit_sphere(S, p, r, tmin, tmax, is_origin, t);
+    }
+    return hit_box(S, p, r, tmin, tmax, is_origin ? origin_face : -1, t, face);
+}
+
+// ------------------------------------------------------------------ BVH traversal
+RTB_DEV int pack_link(int a, int b) { return b > 0 ? ~(a | (b << 24)) : a; }
+
+RTB_DEV bool slab_node(const float4& n0, const float4& n1, V3 o, V3 inv, float tmin, float tmax, float& tn_out) {
+    float ax = (n0.x - o.x) * inv.x, bx = (n1.x - o.x) * inv.x;
+    float ay = (n0.y - o.y) * inv.y, by = (n1.y - o.y) * inv.y;
+    float az = (n0.z - o.z) * inv.z, bz = (n1.z - o.z) * inv.z;
+    float tn = fmaxf(fmaxf(fminf(ax, bx), fminf(ay, by)), fmaxf(fminf(az, bz), tmin));
+    float tf = fminf(fminf(fmaxf(ax, bx), fmaxf(ay, by)), fminf(fmaxf(az, bz), tmax));
+    tn_out = tn;
+    return tn <= tf * 1.0000004f;  // slightly conservative: never cull a box the exact slabs would keep
+}
+
+// Closest surface hit with t in [tmin, +inf): replaces HittableList::hit + BHV::hit + the shapes.
+// origin_prim/origin_face identify the primitive the ray starts on (-1 for camera and medium rays).
+RTB_DEV void closest_hit(const DSceneView& S, const Ray& r, float tmin, float tmax, int origin_prim, int origin_face, float& t_best, int& prim_best,
+                         int& face_best) {
+    t_best = tmax, prim_best = -1, face_best = 0;
+    if (S.n_prims == 0) return;
+    V3 inv = v3(1.0f / r.d.x, 1.0f / r.d.y, 1.0f / r.d.z);
+    int stack[RTB_BVH_STACK];
+    int sp = 0;
+    float4 root_hi = ld4(reinterpret_cast<const char*>(S.nodes) + 16);
+    float4 root_lo = ld4(S.nodes);
+    int cur = pack_link((int)as_uint(root_lo.w), (int)as_uint(root_hi.w));
+    for (;;) {
+        if (cur < 0) {
+            int v = ~cur;
+            int first = v & 0xFFFFFF, count = v >> 24;
+            for (int i = first; i < first + count; ++i) {
+                PrimRec p = load_prim(S.prims + i);
+                float t;
+                int face;
+                if (hit_prim(S, p, r, tmin, t_best, i == origin_prim, origin_face, t, face)) t_best = t, prim_best = i, face_best = face;
+            }
+            if (sp == 0) break;
+            cur = stack[--sp];
+        } else {
+            const char* base = reinterpret_cast<const char*>(S.nodes + cur);
+            float4 l0 = ld4(base), l1 = ld4(base + 16), r0 = ld4(base + 32), r1 = ld4(base + 48);
+            float tl, tr;
+            bool hl = slab_node(l0, l1, r.o, inv, tmin, t_best, tl);
+            bool hr = slab_node(r0, r1, r.o, inv, tmin, t_best, tr);
+            int ll = pack_link((int)as_uint(l0.w), (int)as_uint(l1.w));
+            int lr = pack_link((int)as_uint(r0.w), (int)as_uint(r1.w));
+            if (hl && hr) {
+                bool left_first = tl <= tr;
+                stack[sp++] = left_first ? lr : ll;
+                cur = left_first ? ll : lr;
+            } else if (hl) {
+                cur = ll;
+            } else if (hr) {
+                cur = lr;
+            } else {
+                if (sp == 0) break;
+                cur = stack[--sp];
+            }
+        }
+    }
+}
+
+// brute force over a primitive range (test entry point; also cross-checks the BVH)
+RTB_DEV void closest_hit_linear(const DSceneView& S, const Ray& r, float tmin, float tmax, float& t_best, int& prim_best, int& face_best) {
+    t_best = tmax, prim_best = -1, face_best = 0;
+    for (int i = 0; i < S.n_prims; ++i) {
+        PrimRec p = load_prim(S.prims + i);
+        float t;
+        int face;
+        if (hit_prim(S, p, r, tmin, t_best, false, -1, t, face)) t_best = t, prim_best = i, face_best = face;
+    }
+}
+
+// ------------------------------------------------------------------ media (volumes.rs:25-65)
+// deterministic part: the boundary interval clipped to [tmin, tmax]
+RTB_DEV bool medium_interval(const DSceneView& S, const PrimRec& b, const Ray& r, float tmin, float tmax, float& t1, float& t2) {
+    float te, tx;
+    if ((b.meta & PRIM_KIND_MASK) == PRIM_SPHERE) {
+        if (!sphere_interval(S, b, r, te, tx)) return false;
+    } else {
+        Ray ro = to_object_space(S, prim_instance(b), r);
+        int fe, fx;
+        if (!box_slabs(b, ro, -1, te, tx, fe, fx)) return false;
+    }
+    if (!(tx >= te + 0.001f)) return false;  // second boundary.hit(h1.t + 0.001, inf) finds nothing
+    t1 = fmaxf(te, tmin), t2 = fminf(tx, tmax);
+    if (t1 >= t2) return false;
+    t1 = fmaxf(t1, 0.0f);
+    return true;
+}
+
+// free-flight sampling in every medium; keeps the closest event.  u[m] is the uniform of medium m.
+RTB_DEV void sample_media(const DSceneView& S, const Ray& r, float tmin, const float* u, float& t_best, int& medium_best) {
+    medium_best = -1;
+    float len = sqrtf(dot(r.d, r.d));
+    for (int m = 0; m < S.n_media; ++m) {
+        const DMedium* M = S.media + m;
+        PrimRec b = load_prim(&M->boundary);
+        float4 tail = ld4(reinterpret_cast<const char*>(M) + 32);
+        float t1, t2;
+        if (!medium_interval(S, b, r, tmin, t_best, t1, t2)) continue;
+        float inside = (t2 - t1) * len;
+        float dist = tail.x * fast_log(u[m]);  // neg_inv_density * ln(U)
+        if (dist > inside) continue;
+        t_best = t1 + dist / len;
+        medium_best = m;
+    }
+}
+
+// ------------------------------------------------------------------ textures
+RTB_DEV void sphere_uv(V3 n, float& u, float& v) {  // shapes.rs:44-55
+    const float pi = 3.14159265358979f;
+    float theta = acosf(fminf(fmaxf(-n.y, -1.0f), 1.0f));
+    float phi = atan2f(-n.z, n.x) + pi;
+    u = phi / (2.0f * pi), v = theta / pi;
+}
+
+RTB_DEV float perlin_noise(const float* vec, const unsigned short* perm, V3 p) {  // textures.rs:90-134
+    float fx = floorf(p.x), fy = floorf(p.y), fz = floorf(p.z);
+    float u = p.x - fx, v = p.y - fy, w = p.z - fz;
+    int i = (int)fx, j = (int)fy, k = (int)fz;
+    float uu = u * u * (3.0f - 2.0f * u), vv = v * v * (3.0f - 2.0f * v), ww = w * w * (3.0f - 2.0f * w);
+    float accum = 0.0f;
+#pragma unroll
+    for (int di = 0; di < 2; ++di)
+#pragma unroll
+        for (int dj = 0; dj < 2; ++dj)
+#pragma unroll
+            for (int dk = 0; dk < 2; ++dk) {
+                int idx = perm[(i + di) & 1023] ^ perm[1024 + ((j + dj) & 1023)] ^ perm[2048 + ((k + dk) & 1023)];
+                float4 g = ld4(vec + 4 * idx);
+                float wx = u - (float)di, wy = v - (float)dj, wz = w - (float)dk;
+                float bi = di ? uu : 1.0f - uu, bj = dj ? vv : 1.0f - vv, bk = dk ? ww : 1.0f - ww;
+                accum += bi * bj * bk * (wx * g.x + wy * g.y + wz * g.z);
+            }
+    return accum;
+}
+
+RTB_DEV float perlin_turbulence(const float* vec, const unsigned short* perm, V3 p) {  // textures.rs:76-88, depth 7
+    float accum = 0.0f, weight = 1.0f;
+    for (int i = 0; i < 7; ++i) {
+        accum += weight * perlin_noise(vec, perm, p);
+        weight *= 0.5f;
+        p = 2.0f * p;
+    }
+    return fabsf(accum);
+}
+
+RTB_DEV V3 texture_leaf(const DSceneView& S, const DTexture& T, float u, float v, V3 p) {
+    if (T.kind == TEX_NOISE) {  // NoiseTexture::value, textures.rs:163-166 — marble phase on z
+        const float* vec = S.perlin_vec + (size_t)T.a * RTB_PERLIN_POINTS * 4;
+        const unsigned short* perm = S.perlin_perm + (size_t)T.a * RTB_PERLIN_POINTS * 3;
+        float g = 0.5f * (1.0f + sinf(T.scale * p.z + 10.0f * perlin_turbulence(vec, perm, T.scale * p)));
+        return v3(g, g, g);
+    }
+    if (T.kind == TEX_IMAGE) {  // image_texture.rs:16-28 — nearest texel, v flipped
+        const DImage& im = S.images[T.a];
+        u = fminf(fmaxf(u, 0.0f), 1.0f);
+        v = fminf(fmaxf(1.0f - v, 0.0f), 1.0f);
+        int i = (int)(u * (float)im.width), j = (int)(v * (float)im.height);
+        i = i > im.width - 1 ? im.width - 1 : i;
+        j = j > im.height - 1 ? im.height - 1 : j;
+        float rgb[3];
+        image_fetch(im, i, j, rgb);
+        return v3(rgb[0], rgb[1], rgb[2]);
+    }
+    return v3(T.color[0], T.color[1], T.color[2]);
+}
+
+RTB_DEV V3 texture_value(const DSceneView& S, int tex, float u, float v, V3 p) {
+    const DTexture& T = S.texs[tex];
+    if (T.kind == TEX_CHECKER) {  // textures.rs:40-49
+        float sines = sinf(5.0f * p.x) * sinf(5.0f * p.y) * sinf(5.0f * p.z);
+        return texture_leaf(S, S.texs[sines < 0.0f ? T.a : T.b], u, v, p);
+    }
+    return texture_leaf(S, T, u, v, p);
+}
+
+RTB_DEV bool texture_needs_uv(const DSceneView& S, int tex) {
+    const DTexture& T = S.texs[tex];
+    if (T.kind == TEX_IMAGE) return true;
+    if (T.kind == TEX_CHECKER) return S.texs[T.a].kind == TEX_IMAGE || S.texs[T.b].kind == TEX_IMAGE;
+    return false;
+}
+
+// ------------------------------------------------------------------ hit attributes (hittable.rs:18-30 + transforms)
+struct Surface {
+    V3 p, n;
+    float u, v;
+    bool front;
+};
+
+RTB_DEV void surface_at(const DSceneView& S, const PrimRec& P, const Ray& r, float t, int face, bool want_uv, Surface& s) {
+    int inst = prim_instance(P);
+    V3 ng;         // geometric normal in world space (the reference's "outward" one)
+    V3 n_obj_out;  // outward normal in object space (for sphere uv)
+    s.p = r.o + t * r.d;
+    s.u = 0.0f, s.v = 0.0f;
+    if ((P.meta & PRIM_KIND_MASK) == PRIM_SPHERE) {
+        float inv_r = 1.0f / P.v3;  // signed radius flips the normal (shapes.rs:78)
+        ng = (s.p - v3(P.v0, P.v1, P.v2)) * inv_r;
+        n_obj_out = inst ? mul33t(S.inst[inst - 1].rot, ng) : ng;
+        if (want_uv) sphere_uv(n_obj_out, s.u, s.v);
+    } else {
+        int k = face & 3, side = face >> 2;
+        V3 e = v3(k == 0 ? 1.0f : 0.0f, k == 1 ? 1.0f : 0.0f, k == 2 ? 1.0f : 0.0f);  // rects always report +axis
+        float plane = side ? (k == 0 ? P.v3 : (k == 1 ? P.v4 : P.v5)) : (k == 0 ? P.v0 : (k == 1 ? P.v1 : P.v2));
+        if (inst) {
+            ng = mul33(S.inst[inst - 1].rot, e);
+        } else {
+            ng = e;
+            if (k == 0) s.p.x = plane;  // the hit point lies on the plane exactly
+            else if (k == 1) s.p.y = plane;
+            else s.p.z = plane;
+        }
+        if (want_uv) {
+            Ray ro = to_object_space(S, inst, r);
+            V3 po = ro.o + t * ro.d;
+            int a0 = k == 0 ? 1 : 0, a1 = k == 2 ? 1 : 2;
+            float lo0 = a0 == 0 ? P.v0 : P.v1, hi0 = a0 == 0 ? P.v3 : P.v4;
+            float lo1 = a1 == 1 ? P.v1 : P.v2, hi1 = a1 == 1 ? P.v4 : P.v5;
+            s.u = (comp(po, a0) - lo0) / (hi0 - lo0);
+            s.v = (comp(po, a1) - lo1) / (hi1 - lo1);
+        }
+    }
+    if (inst == 0) {
+        s.front = dot(ng, r.d) < 0.0f;
+        s.n = s.front ? ng : -ng;
+    } else {
+        const DInstance& I = S.inst[inst - 1];
+        float d1 = dot(ng, mul33(I.m1, r.d));  // outermost wrapper's face-forward test
+        float d2 = dot(ng, mul33(I.m2, r.d));  // the one below it
+        s.n = d1 < 0.0f ? ng : -ng;
+        // the normal handed up by the inner level is +ng if d2 < 0 else -ng; front_face = it already faced the ray
+        s.front = (d2 < 0.0f) == (d1 < 0.0f);
+    }
+}
+
+// ------------------------------------------------------------------ shading
+struct PathState {
+    Ray ray;
+    V3 beta;          // product of attenuations so far (raytrace.rs:93)
+    int origin_prim;  // primitive the ray starts on, -1 if none
+    int origin_face;
+    int depth;        // rays still allowed (raytrace.rs:87-89)
+};
+
+RTB_DEV V3 background_color(const DSceneView& S, const Ray& r) {  // raytrace.rs:29-35, :44-48
+    if (S.bg_kind == 0) return v3(0.f, 0.f, 0.f);
+    float t = 0.5f * (normalize(r.d).y + 1.0f);
+    return v3((1.0f - t) * S.bg_bottom[0] + t * S.bg_top[0], (1.0f - t) * S.bg_bottom[1] + t * S.bg_top[1],
+              (1.0f - t) * S.bg_bottom[2] + t * S.bg_top[2]);
+}
+
+RTB_DEV V3 material_color(const DSceneView& S, const DMaterial& M, const Surface& s) {
+    if (M.tex < 0) return v3(M.albedo[0], M.albedo[1], M.albedo[2]);
+    return texture_value(S, M.tex, s.u, s.v, s.p);
+}
+
+// Material::scatter / emit at a surface or medium event.  Returns true when the path goes on (ps updated);
+// otherwise `radiance` is the terminal term (emission, or 0 for an absorbed metal reflection).
+RTB_DEV bool scatter(const DSceneView& S, const DMaterial& M, const Surface& s, const float u[4], PathState& ps, int prim, int face, V3& radiance) {
+    V3 dir, att;
+    switch (M.kind) {
+        case MAT_LAMBERTIAN: {  // materials.rs:25-34: normal + in-ball point flipped into the hemisphere
+            V3 b = sample_unit_ball(u[0], u[1], u[2]);
+            if (!(dot(s.n, b) > 0.0f)) b = -b;
+            dir = s.n + b;
+            if (fabsf(dir.x) < 1e-8f && fabsf(dir.y) < 1e-8f && fabsf(dir.z) < 1e-8f) dir = s.n;
+            att = material_color(S, M, s);
+            break;
+        }
+        case MAT_METAL: {  // materials.rs:51-61
+            V3 ud = normalize(ps.ray.d);
+            dir = ud - (2.0f * dot(ud, s.n)) * s.n;
+            if (M.fuzz > 0.0f) dir = dir + M.fuzz * sample_unit_ball(u[0], u[1], u[2]);
+            if (!(dot(dir, s.n) > 0.0f)) {
+                radiance = v3(0.f, 0.f, 0.f);  // scatter -> None, emit -> 0
+                return false;
+            }
+            att = v3(M.albedo[0], M.albedo[1], M.albedo[2]);
+            break;
+        }
+        case MAT_DIELECTRIC: {  // materials.rs:88-106
+            float ratio = s.front ? 1.0f / M.ior : M.ior;
+            V3 ud = normalize(ps.ray.d);
+            float cos_t = fminf(dot(-ud, s.n), 1.0f);
+            float sin_t = sqrtf(fmaxf(0.0f, 1.0f - cos_t * cos_t));
+            float r0 = (1.0f - ratio) / (1.0f + ratio);
+            r0 = r0 * r0;
+            float x = 1.0f - cos_t;
+            float x2 = x * x;
+            float refl = r0 + (1.0f - r0) * (x * x2 * x2);
+            if (ratio * sin_t > 1.0f || refl > u[3]) {
+                dir = ud - (2.0f * dot(ud, s.n)) * s.n;
+            } else {
+                V3 perp = ratio * (ud + cos_t * s.n);
+                V3 par = -sqrtf(fabsf(1.0f - dot(perp, perp))) * s.n;
+                dir = perp + par;
+            }
+            att = v3(1.f, 1.f, 1.f);
+            break;
+        }
+        case MAT_ISOTROPIC: {  // volumes.rs:77-83: raw in-ball direction
+            dir = sample_unit_ball(u[0], u[1], u[2]);
+            att = material_color(S, M, s);
+            break;
+        }
+        default: {  // MAT_DIFFUSE_LIGHT, materials.rs:119-127: emits from both faces, never scatters
+            radiance = material_color(S, M, s);
+            return false;
+        }
+    }
+    ps.beta = ps.beta * att;
+    ps.ray.o = s.p;
+    ps.ray.d = dir;
+    ps.origin_prim = prim;
+    ps.origin_face = face;
+    return true;
+}
+
+// One path segment: nearest surface, media, then scatter.  Returns true while the path is alive; when it
+// ends, `radiance` holds beta * terminal term.
+RTB_DEV bool extend_and_shade(const DSceneView& S, PathState& ps, PathRng& rng, V3& radiance) {
+    if (ps.depth <= 0) {  // depth exhausted: Color::ZERO (raytrace.rs:87-89)
+        radiance = v3(0.f, 0.f, 0.f);
+        return false;
+    }
+    ps.depth -= 1;
+    float t;
+    int prim, face;
+    closest_hit(S, ps.ray, RTB_T_MIN, RTB_INF, ps.origin_prim, ps.origin_face, t, prim, face);
+    int medium = -1;
+    if (S.n_media > 0) {
+        float um[4];
+        rng_next4(rng, um);
+        sample_media(S, ps.ray, RTB_T_MIN, um, t, medium);
+    }
+    if (prim < 0 && medium < 0) {
+        radiance = ps.beta * background_color(S, ps.ray);
+        return false;
+    }
+    float us[4];
+    rng_next4(rng, us);
+    Surface s;
+    V3 term;
+    bool alive;
+    if (medium >= 0) {  // volumes.rs:55-63: normal (1,0,0), front_face, u = v = 0
+        const DMedium* M = S.media + medium;
+        float4 tail = ld4(reinterpret_cast<const char*>(M) + 32);
+        const DMaterial& mat = S.mats[(int)as_uint(tail.y)];
+        s.p = ps.ray.o + t * ps.ray.d;
+        s.n = v3(1.f, 0.f, 0.f), s.u = 0.f, s.v = 0.f, s.front = true;
+        alive = scatter(S, mat, s, us, ps, -1, 0, term);
+    } else {
+        PrimRec P = load_prim(S.prims + prim);
+        const DMaterial& mat = S.mats[P.mat];
+        bool want_uv = mat.tex >= 0 && texture_needs_uv(S, mat.tex);
+        surface_at(S, P, ps.ray, t, face, want_uv, s);
+        alive = scatter(S, mat, s, us, ps, prim, face, term);
+    }
+    if (!alive) {
+        radiance = ps.beta * term;
+    } else if (ps.depth <= 0) {  // the next trace_internal call would return Color::ZERO at once
+        radiance = v3(0.f, 0.f, 0.f);
+        alive = false;
+    }
+    return alive;
+}
+
+// ------------------------------------------------------------------ one work item = one pixel x a run of samples
+// item -> (tile, lane): a warp covers an 8x4 pixel tile so that its 32 camera rays start coherent.
+RTB_DEV bool item_to_pixel(const DRenderParams& P, long long item, int& px, int& py, int& chunk) {
+    long long per_chunk = (long long)P.tiles_x * P.tiles_y * 32;
+    chunk = (int)(item / per_chunk);
+    int rest = (int)(item - (long long)chunk * per_chunk);
+    int tile = rest >> 5, lane = rest & 31;
+    int tx = tile % P.tiles_x, ty = tile / P.tiles_x;
+    px = tx * 8 + (lane & 7), py = ty * 4 + (lane >> 3);
+    return px < P.width && py < P.height && chunk < P.items_per_pixel;
+}
+
+// render_pixel's sample loop (raytrace.rs:188-198) for samples [first, first + count) of one pixel.
+// Paths are regenerated in place: every loop iteration advances whatever path the thread currently holds by
+// one segment, so the lanes of a warp stay busy until their whole run of samples is finished.
+RTB_DEV void integrate_item(const DSceneView& S, const DCamera& cam, const DRenderParams& P, int px, int py, int first, int count, float sum[3],
+                            uint32_t& n_rays) {
+    PathRng rng;
+    rng.pixel = (uint32_t)(py * P.width + px);
+    rng.k0 = P.seed_lo, rng.k1 = P.seed_hi;
+    rng.sample = 0, rng.draw = 0;
+    PathState ps;
+    ps.depth = 0, ps.origin_prim = -1, ps.origin_face = 0;
+    ps.beta = v3(0.f, 0.f, 0.f);
+    ps.ray.o = ps.ray.d = v3(0.f, 0.f, 0.f);
+    V3 acc = v3(0.f, 0.f, 0.f);
+    bool alive = false;
+    int next = 0;
+    for (;;) {
+        if (!alive) {
+            if (next == count) break;
+            rng.sample = (uint32_t)(first + next), rng.draw = 0;
+            next += 1;
+            float u[4];
+            rng_next4(rng, u);
+            ps.ray = generate_camera_ray(cam, P, px, py, u);
+            ps.beta = v3(1.f, 1.f, 1.f);
+            ps.origin_prim = -1, ps.origin_face = 0;
+            ps.depth = P.max_depth;
+            alive = true;
+        }
+        V3 radiance;
+        n_rays += ps.depth > 0 ? 1u : 0u;
+        alive = extend_and_shade(S, ps, rng, radiance);
+        if (!alive) acc = acc + radiance;
+    }
+    sum[0] = acc.x, sum[1] = acc.y, sum[2] = acc.z;
+}
+
+// ------------------------------------------------------------------ test entry points (rt_intersect_batch etc.)
+enum { QUERY_BVH = 0, QUERY_LINEAR = 1, QUERY_MEDIUM = 2 };
+
+// Hittable::hit for one ray given as 8 floats (origin, direction, t_min, t_max) -> RtHit
+RTB_DEV void intersect_query(const DSceneView& S, int mode, const float* q, RtHit& out) {
+    Ray r;
+    r.o = v3(q[0], q[1], q[2]), r.d = v3(q[3], q[4], q[5]);
+    float tmin = q[6], tmax = q[7];
+    out.t = 0.f, out.u = 0.f, out.v = 0.f, out.front_face = 0, out.material = -1, out.prim = -1;
+    out.p[0] = out.p[1] = out.p[2] = 0.f;
+    out.normal[0] = out.normal[1] = out.normal[2] = 0.f;
+    if (mode == QUERY_MEDIUM) {
+        PrimRec b = load_prim(&S.media[0].boundary);
+        float t1, t2;
+        if (medium_interval(S, b, r, tmin, tmax, t1, t2)) out.t = t1, out.u = t2, out.material = S.media[0].mat;
+        return;
+    }
+    float t;
+    int prim, face;
+    if (mode == QUERY_BVH) closest_hit(S, r, tmin, tmax, -1, 0, t, prim, face);
+    else closest_hit_linear(S, r, tmin, tmax, t, prim, face);
+    if (prim < 0) return;
+    PrimRec P = load_prim(S.prims + prim);
+    Surface s;
+    surface_at(S, P, r, t, face, true, s);
+    out.t = t, out.u = s.u, out.v = s.v, out.front_face = s.front ? 1 : 0, out.material = P.mat, out.prim = prim;
+    out.p[0] = s.p.x, out.p[1] = s.p.y, out.p[2] = s.p.z;
+    out.normal[0] = s.n.x, out.normal[1] = s.n.y, out.normal[2] = s.n.z;
+}
+
+// the camera ray of (pixel, sample) exactly as integrate_item generates it
+RTB_DEV void camera_query(const DCamera& cam, const DRenderParams& P, int pixel, int sample, float* ray6, float* u4) {
+    PathRng rng;
+    rng.pixel = (uint32_t)pixel, rng.sample = (uint32_t)sample, rng.draw = 0, rng.k0 = P.seed_lo, rng.k1 = P.seed_hi;
+    rng_next4(rng, u4);
+    Ray r = generate_camera_ray(cam, P, pixel % P.width, pixel / P.width, u4);
+    ray6[0] = r.o.x, ray6[1] = r.o.y, ray6[2] = r.o.z, ray6[3] = r.d.x, ray6[4] = r.d.y, ray6[5] = r.d.z;
+}
+
+}  // namespace rtb

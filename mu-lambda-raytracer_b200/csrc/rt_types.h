@@ -1,0 +1,137 @@
+// Flattened scene layout shared by the host flattener (flatten.cpp) and the device code (rt_device.cuh).
+//
+// Everything the render loop touches per ray is a 32-byte record fetched as two 128-bit loads:
+//   DNode  — one BVH node  (replaces the boxed `enum Node` tree of src/bhv.rs:103-106)
+//   DPrim  — one primitive (replaces the Sphere / XYRect / XZRect / YZRect / Block trait objects of
+//            src/shapes.rs, with Translate/Rotate of src/transforms.rs folded into an instance record)
+// The whole C4 scene is ~1.4 k primitives + ~1 k nodes ≈ 80 KB, i.e. L1/L2 resident; HBM only ever sees the
+// accumulation buffer.
+#pragma once
+#include <stdint.h>
+
+namespace rtb {
+
+// ---- BVH node, 32 B.  Children of an inner node are adjacent (left = a, right = a + 1) so one 64-byte
+// fetch brings both child boxes; the box of a node lives in the node itself.
+struct alignas(16) DNode {
+    float lo[3];
+    int32_t a;  // inner: index of the left child;   leaf: first primitive
+    float hi[3];
+    int32_t b;  // inner: 0;                         leaf: primitive count (> 0)
+};
+
+enum { PRIM_SPHERE = 0, PRIM_BOX = 1 };
+enum {
+    PRIM_KIND_MASK = 0x3,
+    PRIM_BIG = 0x4,            // sphere evaluated in f64 (|r| >= BIG_SPHERE_RADIUS); v[4] = index into big[]
+    PRIM_INST_SHIFT = 4,       // bits 4..15: instance index + 1 (0 = world space)
+    PRIM_INST_MASK = 0xFFF,
+    PRIM_RECT_SHIFT = 16,      // bits 16..17: plane axis + 1 of an XY/XZ/YZ rect stored as a flat box (0 = Block)
+    PRIM_RECT_MASK = 0x3,
+};
+
+// ---- primitive, 32 B
+//   sphere: v = cx, cy, cz, r (signed), [big index bits], 0      (centre already in world space)
+//   box:    v = min.xyz, max.xyz in OBJECT space (rects are boxes with min == max on the plane axis)
+struct alignas(16) DPrim {
+    float v[6];
+    uint32_t meta;
+    int32_t mat;  // index into materials (== index in the description)
+};
+
+struct DBigSphere {
+    double c[3];
+    double r;
+};
+
+// ---- rigid instance: the composed Translate/Rotate chain above a primitive (transforms.rs).
+//   rot/trans: object -> world (p_w = rot * p_o + trans).  m1/m2 reproduce how the reference re-applies
+//   face-forwarding at the two outermost wrappers (transforms.rs:38,138): the final normal is the sign of
+//   the geometric normal n with dot(n, m1*d) < 0, and front_face tells whether the sign chosen one level
+//   further in (dot(n, m2*d) < 0) already agreed with it.
+struct alignas(16) DInstance {
+    float rot[9];
+    float trans[3];
+    float m1[9];
+    float m2[9];
+    float pad[2];
+};
+
+enum { MAT_LAMBERTIAN = 1, MAT_METAL = 2, MAT_DIELECTRIC = 3, MAT_DIFFUSE_LIGHT = 4, MAT_ISOTROPIC = 5 };
+struct alignas(16) DMaterial {
+    int32_t kind;
+    int32_t tex;  // -1: solid colour folded into albedo
+    float fuzz;
+    float ior;
+    float albedo[3];
+    int32_t pad;
+};
+
+enum { TEX_SOLID = 1, TEX_CHECKER = 2, TEX_NOISE = 3, TEX_IMAGE = 4 };
+struct alignas(16) DTexture {
+    int32_t kind;
+    int32_t a, b;  // CHECKER: odd/even texture; NOISE: perlin table; IMAGE: image
+    float scale;
+    float color[3];
+    int32_t pad;
+};
+
+// ---- constant-density medium (volumes.rs:7-65): boundary primitive + isotropic phase material
+struct alignas(16) DMedium {
+    DPrim boundary;
+    float neg_inv_density;
+    int32_t mat;
+    int32_t desc_node;
+    int32_t pad;
+};
+
+struct DCamera {  // camera.rs:3-12, computed on the host in f64 by Camera::new's formulas
+    float origin[3];
+    float lower_left[3];  // lower_left_corner - origin
+    float horizontal[3];
+    float vertical[3];
+    float u[3];
+    float v[3];
+    float lens_radius;
+};
+
+#define RTB_PERLIN_POINTS 1024
+#define RTB_MAX_MEDIA 4
+#define RTB_BVH_STACK 48
+#define RTB_BIG_SPHERE_RADIUS 100.0
+
+struct DImage {
+    unsigned long long tex;  // cudaTextureObject_t (device) / const uint8_t* RGBA8 (host emulation)
+    int32_t width, height;
+};
+
+// what every kernel receives by value
+struct DSceneView {
+    const DNode* nodes;
+    const DPrim* prims;
+    const DBigSphere* big;
+    const DInstance* inst;
+    const DMaterial* mats;
+    const DTexture* texs;
+    const DMedium* media;
+    const float* perlin_vec;          // n_perlin x 1024 x 4 floats (xyz, pad)
+    const unsigned short* perlin_perm;  // n_perlin x 3 x 1024
+    const DImage* images;
+    int32_t n_nodes, n_prims, n_media, n_perlin;
+    int32_t bg_kind;
+    float bg_top[3];
+    float bg_bottom[3];
+};
+
+struct DRenderParams {
+    int32_t width, height;
+    int32_t max_depth;
+    int32_t sample_begin;     // first sample index of this launch
+    int32_t samples_per_item; // consecutive samples integrated by one thread
+    int32_t items_per_pixel;  // number of sample chunks in this launch
+    int32_t tiles_x, tiles_y; // 8x4 pixel tiles
+    uint32_t seed_lo, seed_hi;
+    float inv_wm1, inv_hm1;   // 1/(W-1), 1/(H-1)  (raytrace.rs:191-192)
+};
+
+}  // namespace rtb

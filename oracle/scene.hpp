@@ -76,6 +76,7 @@ struct Counters {
 struct Ctx {
     Pcg64 rng;
     Counters c;
+    bool skip_media = false;  // parity harness only: surfaces-only closest hit (media are stochastic)
 };
 
 // vec.rs:15-52 samplers
@@ -595,6 +596,7 @@ struct ConstantMedium : Hittable {
         return true;
     }
     bool hit(const Ray& r, double t_min, double t_max, Ctx& cx, Hit& out) const override {
+        if (cx.skip_media) return false;
         cx.c.medium_tests++;
         double t1, t2;
         if (!interval(r, t_min, t_max, cx, t1, t2)) return false;

@@ -1,0 +1,237 @@
+"""Shared test plumbing: the oracle (oracle/liboracle.so), the host emulation of the device header
+(tests/emul/libemul.so) and small helpers.  Both libraries are TEST infrastructure; the product never loads them."""
+import ctypes as C
+import os
+import subprocess
+
+import numpy as np
+
+import mu_lambda_raytracer_b200 as rt
+from mu_lambda_raytracer_b200 import abi
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+GOLDEN = os.path.join(ROOT, "tests", "golden")
+
+
+class OrcHit(C.Structure):
+    _fields_ = [("hit", C.c_int32), ("front_face", C.c_int32), ("material", C.c_int32), ("node", C.c_int32),
+                ("t", C.c_double), ("u", C.c_double), ("v", C.c_double), ("p", C.c_double * 3),
+                ("normal", C.c_double * 3)]
+
+
+_oracle = None
+_emul = None
+
+
+def oracle():
+    global _oracle
+    if _oracle is None:
+        path = os.path.join(ROOT, "oracle", "liboracle.so")
+        srcs = [os.path.join(ROOT, "oracle", f) for f in ("capi.cpp", "pcg64.hpp", "scene.hpp", "worlds.hpp", "render.hpp")]
+        if not os.path.exists(path) or any(os.path.getmtime(s) > os.path.getmtime(path) for s in srcs):
+            subprocess.check_call(["make", "-C", os.path.join(ROOT, "oracle")], stdout=subprocess.DEVNULL)
+        L = C.CDLL(path)
+        L.orc_world_build.restype = C.c_void_p
+        L.orc_world_build.argtypes = [C.c_char_p, C.c_uint64, C.c_void_p, C.c_int, C.c_int]
+        L.orc_world_from_desc.restype = C.c_void_p
+        L.orc_world_from_desc.argtypes = [C.POINTER(abi.RtSceneDesc), C.c_uint64]
+        L.orc_world_free.argtypes = [C.c_void_p]
+        L.orc_world_desc.restype = C.POINTER(abi.RtSceneDesc)
+        L.orc_world_desc.argtypes = [C.c_void_p]
+        L.orc_world_info.argtypes = [C.c_void_p, C.POINTER(C.c_double), C.POINTER(C.c_double), C.POINTER(C.c_double),
+                                     C.POINTER(C.c_int32), C.POINTER(C.c_uint64), C.POINTER(C.c_int32)]
+        L.orc_world_bvh_axes.argtypes = [C.c_void_p, C.c_int32, C.c_void_p, C.c_int32]
+        L.orc_render.restype = C.c_double
+        L.orc_render.argtypes = [C.c_void_p, C.POINTER(abi.RtCamera), C.c_int32, C.c_int32, C.c_int32, C.c_int32,
+                                 C.c_uint64, C.c_int32, C.c_int32, C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p]
+        L.orc_hit_batch.argtypes = [C.c_void_p, C.c_int32, C.c_void_p, C.c_int64, C.c_uint64, C.c_int32, C.c_void_p]
+        L.orc_medium_interval_batch.argtypes = [C.c_void_p, C.c_int32, C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p]
+        L.orc_pcg_seed_stream.argtypes = [C.c_uint64, C.c_int32, C.c_void_p]
+        L.orc_pcg_new_stream.argtypes = [C.c_uint64, C.c_uint64, C.c_uint64, C.c_uint64, C.c_int32, C.c_void_p]
+        L.orc_pcg_from_seed_first.restype = C.c_uint64
+        L.orc_pcg_from_seed_first.argtypes = [C.c_void_p]
+        L.orc_pcg_f64_stream.argtypes = [C.c_uint64, C.c_double, C.c_double, C.c_int32, C.c_void_p]
+        L.orc_pcg_usize_stream.restype = C.c_uint64
+        L.orc_pcg_usize_stream.argtypes = [C.c_uint64, C.c_uint64, C.c_uint64, C.c_int32, C.c_void_p]
+        L.orc_sphere_uv.argtypes = [C.c_void_p, C.c_void_p]
+        L.orc_aabb_hit.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_double, C.c_double]
+        L.orc_aabb_corners.argtypes = [C.c_void_p] * 4
+        L.orc_to_rgb.argtypes = [C.c_void_p, C.c_int32, C.c_void_p]
+        L.orc_camera_ray.argtypes = [C.POINTER(abi.RtCamera), C.c_double, C.c_double, C.c_uint64, C.c_void_p, C.c_void_p]
+        L.orc_camera_basis.argtypes = [C.POINTER(abi.RtCamera), C.c_void_p]
+        L.orc_texture_value.argtypes = [C.c_void_p, C.c_int32, C.c_void_p, C.c_int64, C.c_void_p]
+        L.orc_hardware_threads.restype = C.c_int32
+        _oracle = L
+    return _oracle
+
+
+def emul():
+    """Device header compiled for the host (tests/emul/emul.cpp); CPU-only debugging aid for the device math."""
+    global _emul
+    if _emul is None:
+        path = os.path.join(ROOT, "tests", "emul", "libemul.so")
+        csrc = os.path.join(ROOT, "mu-lambda-raytracer_b200", "csrc")
+        srcs = [os.path.join(ROOT, "tests", "emul", "emul.cpp")] + [os.path.join(csrc, f) for f in
+                                                                     ("flatten.cpp", "flatten.h", "rt_device.cuh", "rt_types.h")]
+        if not os.path.exists(path) or any(os.path.getmtime(s) > os.path.getmtime(path) for s in srcs):
+            subprocess.check_call(["g++", "-O2", "-std=c++17", "-fPIC", "-pthread", "-w", "-shared", "-o", path,
+                                   srcs[0], srcs[1]])
+        L = C.CDLL(path)
+        L.emul_last_error.restype = C.c_char_p
+        L.emul_scene_create.restype = C.c_void_p
+        L.emul_scene_create.argtypes = [C.POINTER(abi.RtSceneDesc), C.c_int32, C.c_int32]
+        L.emul_scene_destroy.argtypes = [C.c_void_p]
+        L.emul_scene_info.argtypes = [C.c_void_p] + [C.POINTER(C.c_int32)] * 4
+        L.emul_prim_nodes.argtypes = [C.c_void_p, C.c_void_p, C.c_int32]
+        L.emul_intersect_batch.argtypes = [C.c_void_p, C.c_int32, C.c_void_p, C.c_int64, C.c_void_p]
+        L.emul_texture_value_batch.argtypes = [C.c_void_p, C.c_int32, C.c_void_p, C.c_int64, C.c_void_p]
+        L.emul_generate_rays.argtypes = [C.POINTER(abi.RtCamera), C.POINTER(abi.RtParams), C.c_void_p, C.c_void_p,
+                                         C.c_int64, C.c_void_p, C.c_void_p]
+        L.emul_philox.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p]
+        L.emul_unit_ball.argtypes = [C.c_void_p, C.c_int64, C.c_void_p]
+        L.emul_render.restype = C.c_uint64
+        L.emul_render.argtypes = [C.c_void_p, C.POINTER(abi.RtCamera), C.POINTER(abi.RtParams), C.c_int32, C.c_void_p]
+        _emul = L
+    return _emul
+
+
+_earth = None
+
+
+def earthmap():
+    global _earth
+    if _earth is None:
+        _earth = rt.load_earthmap()
+    return _earth
+
+
+class OracleWorld:
+    def __init__(self, name=None, seed=42, desc=None, bvh_seed=1):
+        L = oracle()
+        if desc is not None:
+            self._keep = desc
+            self.h = L.orc_world_from_desc(desc, bvh_seed)
+        else:
+            e = earthmap()
+            self.h = L.orc_world_build(name.encode(), seed, e.ctypes.data, e.shape[1], e.shape[0])
+        if not self.h:
+            raise RuntimeError("oracle could not build the world")
+        lf, la = (C.c_double * 3)(), (C.c_double * 3)()
+        fov, bg, dr, nb = C.c_double(), C.c_int32(), C.c_uint64(), C.c_int32()
+        L.orc_world_info(self.h, lf, la, C.byref(fov), C.byref(bg), C.byref(dr), C.byref(nb))
+        self.lookfrom, self.lookat, self.vfov = tuple(lf), tuple(la), fov.value
+        self.background, self.draws, self.n_bvh = bg.value, dr.value, nb.value
+
+    @property
+    def desc(self):
+        return oracle().orc_world_desc(self.h)
+
+    def bvh_axes(self, which):
+        L = oracle()
+        n = L.orc_world_bvh_axes(self.h, which, None, 0)
+        out = np.zeros(n, dtype=np.int32)
+        L.orc_world_bvh_axes(self.h, which, out.ctypes.data, n)
+        return out
+
+    def hit(self, rays, node=-1, rng_seed=7, skip_media=True):
+        rays = np.ascontiguousarray(rays, dtype=np.float64)
+        out = (OrcHit * len(rays))()
+        rc = oracle().orc_hit_batch(self.h, node, rays.ctypes.data, len(rays), rng_seed, 1 if skip_media else 0, out)
+        assert rc == 0
+        return np.ctypeslib.as_array(out)
+
+    def medium_interval(self, rays, node):
+        rays = np.ascontiguousarray(rays, dtype=np.float64)
+        hit = np.zeros(len(rays), dtype=np.int32)
+        t = np.zeros((len(rays), 2), dtype=np.float64)
+        rc = oracle().orc_medium_interval_batch(self.h, node, rays.ctypes.data, len(rays), hit.ctypes.data, t.ctypes.data)
+        assert rc == 0
+        return hit, t
+
+    def render(self, cam, width, height, spp, max_depth=50, render_seed=42, rows=None, threads=0, want_rgb=True):
+        accum = np.zeros((height, width, 3), dtype=np.float64)
+        rgb = np.zeros((height, width, 3), dtype=np.int32)
+        counters = np.zeros(16, dtype=np.uint64)
+        r0, r1 = rows if rows else (0, -1)
+        secs = oracle().orc_render(self.h, C.byref(cam), width, height, spp, max_depth, render_seed, r0, r1, threads,
+                                   accum.ctypes.data, rgb.ctypes.data, counters.ctypes.data)
+        return accum, rgb, counters, secs
+
+    def close(self):
+        if self.h:
+            oracle().orc_world_free(self.h)
+            self.h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+
+COUNTER_NAMES = ["paths", "rays", "aabb", "sphere", "rect", "xform", "medium", "lambertian", "metal", "dielectric",
+                 "light", "isotropic", "perlin", "image", "background", "depth_exhausted"]
+
+
+def make_camera(lookfrom, lookat, vfov, aspect, aperture=0.0, focus_dist=None, vup=(0, 1, 0)):
+    if focus_dist is None:  # main.rs:109-112
+        focus_dist = float(np.linalg.norm(np.asarray(lookat, float) - np.asarray(lookfrom, float)))
+    return rt.Camera(lookfrom, lookat, vup, vfov, aspect, aperture, focus_dist)
+
+
+class EmulScene:
+    def __init__(self, desc_ptr, root=-1, build_bvh=True):
+        L = emul()
+        self._keep = desc_ptr
+        self.h = L.emul_scene_create(desc_ptr, root, 1 if build_bvh else 0)
+        if not self.h:
+            raise RuntimeError("emul: " + L.emul_last_error().decode())
+        a, b, c, d = C.c_int32(), C.c_int32(), C.c_int32(), C.c_int32()
+        L.emul_scene_info(self.h, C.byref(a), C.byref(b), C.byref(c), C.byref(d))
+        self.n_prims, self.n_nodes, self.n_media, self.depth = a.value, b.value, c.value, d.value
+        self.prim_nodes = np.zeros(max(self.n_prims, 1), dtype=np.int32)
+        L.emul_prim_nodes(self.h, self.prim_nodes.ctypes.data, self.n_prims)
+
+    def intersect(self, rays, mode=0):
+        rays = np.ascontiguousarray(rays, dtype=np.float32)
+        out = (abi.RtHit * len(rays))()
+        emul().emul_intersect_batch(self.h, mode, rays.ctypes.data, len(rays), out)
+        a = np.ctypeslib.as_array(out).copy()
+        ok = a["prim"] >= 0
+        a["prim"][ok] = self.prim_nodes[a["prim"][ok]]
+        return a
+
+    def render(self, cam, width, height, spp, max_depth=50, seed=42, threads=0, sample_begin=0):
+        p = abi.RtParams()
+        p.width, p.height, p.samples_per_pixel, p.max_depth = width, height, spp, max_depth
+        p.seed, p.sample_begin, p.sample_count = seed, sample_begin, spp
+        accum = np.zeros((height, width, 3), dtype=np.float32)
+        rays = emul().emul_render(self.h, C.byref(cam.c), C.byref(p), threads, accum.ctypes.data)
+        return accum, rays
+
+    def close(self):
+        if self.h:
+            emul().emul_scene_destroy(self.h)
+            self.h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+
+def random_rays(n, rng, lo, hi, tmin=0.001, tmax=np.inf, target=None, spread=None):
+    """n rays with origins uniform in the box [lo, hi] and NON-unit directions; with `target`, directions aim at
+    a point jittered by `spread` around it (so that small objects get hit often)."""
+    o = rng.uniform(lo, hi, size=(n, 3))
+    if target is None:
+        d = rng.normal(size=(n, 3))
+    else:
+        aim = np.asarray(target, float) + rng.uniform(-1, 1, size=(n, 3)) * np.asarray(spread, float)
+        d = aim - o
+    d *= rng.uniform(0.05, 3.0, size=(n, 1)) / np.linalg.norm(d, axis=1, keepdims=True)
+    r = np.zeros((n, 8))
+    r[:, 0:3], r[:, 3:6], r[:, 6], r[:, 7] = o, d, tmin, tmax
+    # the device sees f32 rays: make the f64 oracle see exactly the same numbers
+    return r.astype(np.float32).astype(np.float64)
