@@ -183,7 +183,7 @@ def probe_published_renders(spheres):
             continue
         x, y, depth = pr
         rad_px = 0.2 / depth / (2 * math.tan(math.radians(10.0))) * (H - 1)
-        if rad_px < 5 or not (8 <= x < W - 8 and 8 <= y < H - 8):
+        if rad_px < 4 or not (8 <= x < W - 8 and 8 <= y < H - 8):
             continue
         # unoccluded: no other sphere centre projects within 1.6 radii and is closer
         occluded = False
@@ -191,13 +191,13 @@ def probe_published_renders(spheres):
             if k2 == idx:
                 continue
             p2 = camera_project(lookfrom, lookat, 20.0, 1.5, W, H, c2)
-            if p2 and p2[2] < depth and math.hypot(p2[0] - x, p2[1] - y) < 2.2 * rad_px:
+            if p2 and p2[2] < depth and math.hypot(p2[0] - x, p2[1] - y) < 1.6 * rad_px:
                 occluded = True
                 break
         for bc in ([0, 1, 0], [-4, 1, 0], [4, 1, 0]):
             p2 = camera_project(lookfrom, lookat, 20.0, 1.5, W, H, bc)
             r2 = 1.0 / p2[2] / (2 * math.tan(math.radians(10.0))) * (H - 1)
-            if p2[2] < depth and math.hypot(p2[0] - x, p2[1] - y) < r2 + 1.5 * rad_px:
+            if p2[2] < depth and math.hypot(p2[0] - x, p2[1] - y) < r2 + 1.0 * rad_px:
                 occluded = True
         if occluded:
             continue

@@ -235,3 +235,121 @@ def random_rays(n, rng, lo, hi, tmin=0.001, tmax=np.inf, target=None, spread=Non
     r[:, 0:3], r[:, 3:6], r[:, 6], r[:, 7] = o, d, tmin, tmax
     # the device sees f32 rays: make the f64 oracle see exactly the same numbers
     return r.astype(np.float32).astype(np.float64)
+
+
+class DescBuilder:
+    """Builds ad-hoc RtSceneDesc's for the per-primitive parity tests (the same struct the product builder emits)."""
+
+    def __init__(self):
+        self.nodes, self.children, self.materials, self.textures, self.perlins, self.images = [], [], [], [], [], []
+        self._keep = []
+
+    def solid(self, r, g, b):
+        t = abi.RtTexture()
+        t.kind, t.a, t.b = abi.RT_TEX_SOLID, -1, -1
+        t.color[0], t.color[1], t.color[2] = r, g, b
+        self.textures.append(t)
+        return len(self.textures) - 1
+
+    def checker(self, odd, even):
+        t = abi.RtTexture()
+        t.kind, t.a, t.b = abi.RT_TEX_CHECKER, odd, even
+        self.textures.append(t)
+        return len(self.textures) - 1
+
+    def noise(self, scale, perlin_from=None, seed=3):
+        """perlin tables: copied from another description, or random unit vectors + permutations"""
+        p = abi.RtPerlin()
+        if perlin_from is not None:
+            C.memmove(C.byref(p), C.byref(perlin_from), C.sizeof(p))
+        else:
+            rng = np.random.default_rng(seed)
+            v = rng.normal(size=(1024, 3))
+            v /= np.linalg.norm(v, axis=1, keepdims=True)
+            for i in range(1024):
+                for c in range(3):
+                    p.ranvec[i][c] = v[i, c]
+            for perm in (p.perm_x, p.perm_y, p.perm_z):
+                for i, x in enumerate(rng.permutation(1024)):
+                    perm[i] = int(x)
+        self.perlins.append(p)
+        t = abi.RtTexture()
+        t.kind, t.a, t.b, t.scale = abi.RT_TEX_NOISE, len(self.perlins) - 1, -1, scale
+        self.textures.append(t)
+        return len(self.textures) - 1
+
+    def image(self, rgb):
+        rgb = np.ascontiguousarray(rgb, dtype=np.uint8)
+        self._keep.append(rgb)
+        im = abi.RtImage()
+        im.width, im.height = rgb.shape[1], rgb.shape[0]
+        im.rgb = rgb.ctypes.data_as(C.POINTER(C.c_uint8))
+        self.images.append(im)
+        t = abi.RtTexture()
+        t.kind, t.a, t.b = abi.RT_TEX_IMAGE, len(self.images) - 1, -1
+        self.textures.append(t)
+        return len(self.textures) - 1
+
+    def material(self, kind, tex=-1, albedo=(0, 0, 0), fuzz=0.0, ior=0.0):
+        m = abi.RtMaterial()
+        m.kind, m.texture, m.fuzz, m.ior = kind, tex, fuzz, ior
+        for i in range(3):
+            m.albedo[i] = albedo[i]
+        self.materials.append(m)
+        return len(self.materials) - 1
+
+    def lambertian(self, tex):
+        return self.material(abi.RT_MAT_LAMBERTIAN, tex)
+
+    def _node(self, kind, mat, f, child=-1, axis=0, count=0):
+        n = abi.RtNode()
+        n.kind, n.material, n.first_child, n.child_count, n.axis = kind, mat, child, count, axis
+        for i, v in enumerate(f):
+            n.f[i] = v
+        self.nodes.append(n)
+        return len(self.nodes) - 1
+
+    def sphere(self, c, r, mat):
+        return self._node(abi.RT_NODE_SPHERE, mat, [c[0], c[1], c[2], r])
+
+    def rect(self, kind, a0, a1, b0, b1, k, mat):
+        return self._node(kind, mat, [a0, a1, b0, b1, k])
+
+    def block(self, p0, p1, mat):
+        return self._node(abi.RT_NODE_BLOCK, mat, list(p0) + list(p1))
+
+    def translate(self, off, child):
+        return self._node(abi.RT_NODE_TRANSLATE, -1, list(off), child)
+
+    def rotate(self, axis, degrees, child):
+        return self._node(abi.RT_NODE_ROTATE, -1, [degrees], child, axis)
+
+    def medium(self, boundary, density, color):
+        iso = self.material(abi.RT_MAT_ISOTROPIC, self.solid(*color))
+        return self._node(abi.RT_NODE_MEDIUM, iso, [density], boundary)
+
+    def group(self, kind, items):
+        first = len(self.children)
+        self.children.extend(items)
+        return self._node(kind, -1, [], first, 0, len(items))
+
+    def finish(self, root, background=abi.RT_BG_BLACK):
+        d = abi.RtSceneDesc()
+        d.root, d.background_kind = root, background
+        if background == abi.RT_BG_GRADIENT:
+            for i, (t, b) in enumerate(zip((0.5, 0.7, 1.0), (1.0, 1.0, 1.0))):
+                d.background_top[i], d.background_bottom[i] = t, b
+
+        def arr(ctype, items):
+            a = (ctype * max(len(items), 1))(*items)
+            self._keep.append(a)
+            return a
+
+        d.n_nodes, d.nodes = len(self.nodes), arr(abi.RtNode, self.nodes)
+        d.n_children, d.children = len(self.children), arr(C.c_int32, self.children)
+        d.n_materials, d.materials = len(self.materials), arr(abi.RtMaterial, self.materials)
+        d.n_textures, d.textures = len(self.textures), arr(abi.RtTexture, self.textures)
+        d.n_perlins, d.perlins = len(self.perlins), arr(abi.RtPerlin, self.perlins)
+        d.n_images, d.images = len(self.images), arr(abi.RtImage, self.images)
+        self.desc = d
+        return C.pointer(d)
