@@ -53,15 +53,16 @@ def build(force=False, verbose=False):
             if verbose and out:
                 print(out)
         objs.append(o)
-    cu = os.path.join(CSRC, "rt_api.cu")
-    cuo = os.path.join(bdir, "rt_api.o")
-    if force or _newer(cuo, [cu] + headers):
-        out = _run([_nvcc()] + NVCC_FLAGS + ["-Xptxas", "-v", "-c", cu, "-o", cuo])
-        with open(os.path.join(bdir, "ptxas.log"), "w") as f:
-            f.write(out)
-        if verbose:
-            print(out)
-    objs.append(cuo)
+    for src in ("rt_api.cu", "rt_wavefront.cu"):
+        cu = os.path.join(CSRC, src)
+        cuo = os.path.join(bdir, src + ".o")
+        if force or _newer(cuo, [cu] + headers):
+            out = _run([_nvcc()] + NVCC_FLAGS + ["-Xptxas", "-v", "-c", cu, "-o", cuo])
+            with open(os.path.join(bdir, src + ".ptxas.log"), "w") as f:
+                f.write(out)
+            if verbose:
+                print(out)
+        objs.append(cuo)
     if force or _newer(OUT, objs):
         _run([_nvcc(), "-shared", "-o", OUT] + objs + ["-gencode", "arch=compute_100a,code=sm_100a", "-cudart", "static"])
     main_src = os.path.join(CSRC, "main.cpp")

@@ -339,7 +339,7 @@ class Flattener {
         bool leaf = n <= kMaxLeaf && (n < 2 || (double)n <= best_cost);
         if (depth >= RTB_BVH_STACK - 2 && n <= 255) leaf = true;  // never outgrow the traversal stack
         if (leaf) {
-            out.nodes[idx].a = begin, out.nodes[idx].b = n;
+            out.nodes[idx].a = ~(begin | (n << 24)), out.nodes[idx].b = n;  // ready-made traversal link
             return;
         }
         std::stable_sort(order.begin() + begin, order.begin() + end, [&](int x, int y) {
@@ -357,7 +357,7 @@ class Flattener {
         out.nodes.clear();
         out.nodes.push_back(DNode{});
         if (n == 0) {  // empty world: a leaf with no primitives
-            out.nodes[0].a = 0, out.nodes[0].b = 0;
+            out.nodes[0].a = ~0, out.nodes[0].b = 0;
             return;
         }
         order.resize(n);

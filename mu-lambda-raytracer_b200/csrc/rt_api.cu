@@ -14,6 +14,7 @@
 #include "flatten.h"
 #include "internal.h"
 #include "rt_device.cuh"
+#include "scene_internal.h"
 
 using namespace rtb;
 
@@ -85,25 +86,6 @@ __global__ void camera_kernel(DCamera cam, DRenderParams P, const int32_t* __res
 
 namespace {
 
-#define CU_TRY(expr)                                                                                         \
-    do {                                                                                                     \
-        cudaError_t e_ = (expr);                                                                             \
-        if (e_ != cudaSuccess) return set_error(RT_ERR_CUDA, "%s failed: %s", #expr, cudaGetErrorString(e_)); \
-    } while (0)
-
-struct DeviceGuard {  // run on the scene's device, restore the caller's afterwards
-    int prev = -1;
-    explicit DeviceGuard(int dev) {
-        cudaGetDevice(&prev);
-        if (dev != prev) cudaSetDevice(dev);
-    }
-    ~DeviceGuard() {
-        int cur = -1;
-        cudaGetDevice(&cur);
-        if (prev >= 0 && cur != prev) cudaSetDevice(prev);
-    }
-};
-
 template <class T>
 int upload(const std::vector<T>& v, T** out, std::vector<void*>& owned, int64_t& bytes) {
     *out = nullptr;
@@ -119,22 +101,6 @@ int upload(const std::vector<T>& v, T** out, std::vector<void*>& owned, int64_t&
 
 }  // namespace
 
-struct RtScene {
-    int device = 0;
-    DSceneView view{};
-    FlatScene flat;  // host copy (info + hit -> description node mapping)
-    std::vector<void*> owned;
-    std::vector<cudaArray_t> arrays;
-    std::vector<cudaTextureObject_t> textures;
-    int64_t device_bytes = 0;
-    rtb::OwnedDesc* desc = nullptr;  // deep copy of the description (sub-tree queries of rt_intersect_batch)
-    // scratch of rt_render (host-buffer entry point), grown on demand
-    float* d_accum = nullptr;
-    int32_t* d_rgb = nullptr;
-    size_t scratch_values = 0;
-    unsigned long long* d_rays = nullptr;
-    cudaEvent_t ev0 = nullptr, ev1 = nullptr;
-};
 
 namespace {
 
@@ -215,6 +181,7 @@ void free_scene(RtScene* s) {
         if (s->d_rays) cudaFree(s->d_rays);
         if (s->ev0) cudaEventDestroy(s->ev0);
         if (s->ev1) cudaEventDestroy(s->ev1);
+        free_wavefront(s);
     }
     if (s->desc) rtb::free_desc(s->desc);
     delete s;
@@ -253,6 +220,9 @@ int validate_render(const RtScene* scene, const RtCamera* cam, const RtParams* p
     return RT_OK;
 }
 
+}  // namespace
+
+namespace rtb {
 DRenderParams device_params(const RtParams* p, int first_sample, int spi, int chunks) {
     DRenderParams P{};
     P.width = p->width, P.height = p->height, P.max_depth = p->max_depth;
@@ -289,6 +259,22 @@ int launch_megakernel(const RtScene* s, const DCamera& cam, const RtParams* p, i
         }
     }
     return RT_OK;
+}
+}  // namespace rtb
+
+namespace {
+
+// AUTO resolves to the pipeline measured fastest on B200 for this scene class (see DESIGN.md "Pipelines")
+int pick_pipeline(const RtScene* s, const RtParams* p) {
+    if (p->pipeline != RT_PIPELINE_AUTO) return p->pipeline;
+    return RT_PIPELINE_WAVEFRONT;
+}
+
+int run_pipeline(RtScene* s, const DCamera& cam, const RtParams* p, int begin, int count, float* d_accum, cudaStream_t stream, RtProgressFn cb,
+                 void* user, int* launches, int* used) {
+    *used = pick_pipeline(s, p);
+    if (*used == RT_PIPELINE_WAVEFRONT) return launch_wavefront(s, cam, p, begin, count, d_accum, stream, cb, user, launches);
+    return launch_megakernel(s, cam, p, begin, count, d_accum, stream, cb, user, launches);
 }
 
 }  // namespace
@@ -330,7 +316,6 @@ int rt_render_accumulate_device(const RtScene* scene, const RtCamera* cam, const
     int rc = validate_render(scene, cam, params);
     if (rc != RT_OK) return rc;
     if (!d_accum_rgb) return set_error(RT_ERR_INVALID, "rt_render_accumulate_device: null accumulation buffer");
-    if (params->pipeline == RT_PIPELINE_WAVEFRONT) return set_error(RT_ERR_UNSUPPORTED, "wavefront pipeline is not built yet");
     cudaStream_t stream = (cudaStream_t)stream_;
     DeviceGuard g(scene->device);
     int begin = params->sample_begin;
@@ -343,7 +328,8 @@ int rt_render_accumulate_device(const RtScene* scene, const RtCamera* cam, const
         CU_TRY(cudaMemsetAsync(scene->d_rays, 0, sizeof(unsigned long long), stream));
         CU_TRY(cudaEventRecord(scene->ev0, stream));
     }
-    rc = launch_megakernel(scene, dc, params, begin, count, d_accum_rgb, stream, nullptr, nullptr, &launches);
+    int used = 0;
+    rc = run_pipeline(const_cast<RtScene*>(scene), dc, params, begin, count, d_accum_rgb, stream, nullptr, nullptr, &launches, &used);
     if (rc != RT_OK) return rc;
     if (stats) {
         CU_TRY(cudaEventRecord(scene->ev1, stream));
@@ -356,7 +342,7 @@ int rt_render_accumulate_device(const RtScene* scene, const RtCamera* cam, const
         stats->rays = rays;
         stats->device_ms = ms;
         stats->kernel_launches = launches;
-        stats->pipeline_used = RT_PIPELINE_MEGAKERNEL;
+        stats->pipeline_used = used;
     }
     return RT_OK;
 }
@@ -377,7 +363,6 @@ int rt_render(const RtScene* scene_, const RtCamera* cam, const RtParams* params
               RtStats* stats) {
     int rc = validate_render(scene_, cam, params);
     if (rc != RT_OK) return rc;
-    if (params->pipeline == RT_PIPELINE_WAVEFRONT) return set_error(RT_ERR_UNSUPPORTED, "wavefront pipeline is not built yet");
     RtScene* scene = const_cast<RtScene*>(scene_);  // scratch buffers are cached in the scene object
     DeviceGuard g(scene->device);
     size_t n_values = (size_t)3 * params->width * params->height;
@@ -399,7 +384,8 @@ int rt_render(const RtScene* scene_, const RtCamera* cam, const RtParams* params
     CU_TRY(cudaMemsetAsync(scene->d_rays, 0, sizeof(unsigned long long), stream));
     CU_TRY(cudaEventRecord(scene->ev0, stream));
     CU_TRY(cudaMemsetAsync(scene->d_accum, 0, n_values * sizeof(float), stream));
-    rc = launch_megakernel(scene, dc, params, begin, count, scene->d_accum, stream, cb, user, &launches);
+    int used = 0;
+    rc = run_pipeline(scene, dc, params, begin, count, scene->d_accum, stream, cb, user, &launches, &used);
     if (rc != RT_OK) return rc;
     tonemap_kernel<<<(unsigned)((n_values + 255) / 256), 256, 0, stream>>>(scene->d_accum, scene->d_rgb, (int)n_values, 1.0 / (double)params->samples_per_pixel);
     CU_TRY(cudaGetLastError());
@@ -417,7 +403,7 @@ int rt_render(const RtScene* scene_, const RtCamera* cam, const RtParams* params
         stats->rays = rays;
         stats->device_ms = ms;
         stats->kernel_launches = launches;
-        stats->pipeline_used = RT_PIPELINE_MEGAKERNEL;
+        stats->pipeline_used = used;
     }
     return RT_OK;
 }

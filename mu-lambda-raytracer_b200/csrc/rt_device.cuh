@@ -331,8 +331,6 @@ RTB_DEV bool hit_prim(const DSceneView& S, const PrimRec& p, const Ray& r, float
 }
 
 // ------------------------------------------------------------------ BVH traversal
-RTB_DEV int pack_link(int a, int b) { return b > 0 ? ~(a | (b << 24)) : a; }
-
 RTB_DEV bool slab_node(const float4& n0, const float4& n1, V3 o, V3 inv, float tmin, float tmax, float& tn_out) {
     float ax = (n0.x - o.x) * inv.x, bx = (n1.x - o.x) * inv.x;
     float ay = (n0.y - o.y) * inv.y, by = (n1.y - o.y) * inv.y;
@@ -352,9 +350,7 @@ RTB_DEV void closest_hit(const DSceneView& S, const Ray& r, float tmin, float tm
     V3 inv = v3(1.0f / r.d.x, 1.0f / r.d.y, 1.0f / r.d.z);
     int stack[RTB_BVH_STACK];
     int sp = 0;
-    float4 root_hi = ld4(reinterpret_cast<const char*>(S.nodes) + 16);
-    float4 root_lo = ld4(S.nodes);
-    int cur = pack_link((int)as_uint(root_lo.w), (int)as_uint(root_hi.w));
+    int cur = (int)as_uint(ld4(S.nodes).w);  // link of the root (its own box is never tested)
     for (;;) {
         if (cur < 0) {
             int v = ~cur;
@@ -373,8 +369,7 @@ RTB_DEV void closest_hit(const DSceneView& S, const Ray& r, float tmin, float tm
             float tl, tr;
             bool hl = slab_node(l0, l1, r.o, inv, tmin, t_best, tl);
             bool hr = slab_node(r0, r1, r.o, inv, tmin, t_best, tr);
-            int ll = pack_link((int)as_uint(l0.w), (int)as_uint(l1.w));
-            int lr = pack_link((int)as_uint(r0.w), (int)as_uint(r1.w));
+            int ll = (int)as_uint(l0.w), lr = (int)as_uint(r0.w);
             if (hl && hr) {
                 bool left_first = tl <= tr;
                 stack[sp++] = left_first ? lr : ll;
@@ -652,7 +647,7 @@ RTB_DEV bool scatter(const DSceneView& S, const DMaterial& M, const Surface& s, 
 
 // One path segment: nearest surface, media, then scatter.  Returns true while the path is alive; when it
 // ends, `radiance` holds beta * terminal term.
-RTB_DEV bool extend_and_shade(const DSceneView& S, PathState& ps, PathRng& rng, V3& radiance) {
+RTB_DEV bool extend_and_shade(const DSceneView& S, PathState& ps, PathRng& rng, int segment, V3& radiance) {
     if (ps.depth <= 0) {  // depth exhausted: Color::ZERO (raytrace.rs:87-89)
         radiance = v3(0.f, 0.f, 0.f);
         return false;
@@ -662,11 +657,15 @@ RTB_DEV bool extend_and_shade(const DSceneView& S, PathState& ps, PathRng& rng, 
     int prim, face;
     closest_hit(S, ps.ray, RTB_T_MIN, RTB_INF, ps.origin_prim, ps.origin_face, t, prim, face);
     int medium = -1;
+    // Philox draw indices are a function of the segment number k alone (camera = 0, media = 1 + 2k, scatter =
+    // 2 + 2k), so the megakernel and the wavefront pipeline consume identical streams.
+    rng.draw = 1u + 2u * (uint32_t)segment;
     if (S.n_media > 0) {
         float um[4];
         rng_next4(rng, um);
         sample_media(S, ps.ray, RTB_T_MIN, um, t, medium);
     }
+    rng.draw = 2u + 2u * (uint32_t)segment;
     if (prim < 0 && medium < 0) {
         radiance = ps.beta * background_color(S, ps.ray);
         return false;
@@ -742,10 +741,129 @@ RTB_DEV void integrate_item(const DSceneView& S, const DCamera& cam, const DRend
         }
         V3 radiance;
         n_rays += ps.depth > 0 ? 1u : 0u;
-        alive = extend_and_shade(S, ps, rng, radiance);
+        alive = extend_and_shade(S, ps, rng, P.max_depth - ps.depth, radiance);
         if (!alive) acc = acc + radiance;
     }
     sum[0] = acc.x, sum[1] = acc.y, sum[2] = acc.z;
+}
+
+// ------------------------------------------------------------------ wavefront path state (rt_wavefront.cu)
+// One pool slot = four 128-bit words:
+//   A = origin.xyz, pixel            B = direction.xyz, flags (depth left | origin face)
+//   C = beta.rgb, -                  D = hit t, hit code, origin primitive, sample index
+// hit code: -1 miss, prim | face << 24 for a surface, WF_MEDIUM | m for a medium event.
+enum { WF_MISS = 0, WF_LAMBERTIAN = 1, WF_METAL = 2, WF_DIELECTRIC = 3, WF_LIGHT = 4, WF_ISOTROPIC = 5, WF_TEXTURED = 6, WF_CLASSES = 7 };
+#define WF_MEDIUM 0x40000000
+#define WF_DEPTH_MASK 0xFFFF
+#define WF_FACE_SHIFT 16
+
+struct WfSlot {
+    float4 A, B, C, D;
+};
+RTB_DEV float4 f4(float x, float y, float z, float w) {
+    float4 v;
+    v.x = x, v.y = y, v.z = z, v.w = w;
+    return v;
+}
+
+// a fresh camera path: global path number -> (pixel, sample); sample-major so that consecutive paths are
+// neighbouring pixels of one sample index
+RTB_DEV void wf_init_path(const DCamera& cam, const DRenderParams& P, unsigned long long path, WfSlot& s) {
+    unsigned long long npix = (unsigned long long)P.width * (unsigned long long)P.height;
+    uint32_t sample = (uint32_t)P.sample_begin + (uint32_t)(path / npix);
+    uint32_t pixel = (uint32_t)(path % npix);
+    PathRng rng;
+    rng.pixel = pixel, rng.sample = sample, rng.draw = 0, rng.k0 = P.seed_lo, rng.k1 = P.seed_hi;
+    float u[4];
+    rng_next4(rng, u);
+    Ray r = generate_camera_ray(cam, P, (int)(pixel % (uint32_t)P.width), (int)(pixel / (uint32_t)P.width), u);
+    s.A = f4(r.o.x, r.o.y, r.o.z, as_float(pixel));
+    s.B = f4(r.d.x, r.d.y, r.d.z, as_float((uint32_t)P.max_depth));
+    s.C = f4(1.f, 1.f, 1.f, 0.f);
+    s.D = f4(0.f, as_float(0xFFFFFFFFu), as_float(0xFFFFFFFFu), as_float(sample));
+}
+
+// end of the extend stage for one ray: media free-flight sampling on top of the surface search, then the queue
+// class the shade stage will pick the path up from.  Returns the class; writes hit t / code.
+RTB_DEV int wf_finish_extend(const DSceneView& S, const DRenderParams& P, const Ray& r, uint32_t pixel, uint32_t sample, uint32_t flags, float t, int prim,
+                             int face, float& t_out, int& code_out) {
+    int medium = -1;
+    if (S.n_media > 0) {
+        int segment = P.max_depth - (int)(flags & WF_DEPTH_MASK);
+        PathRng rng;
+        rng.pixel = pixel, rng.sample = sample, rng.draw = 1u + 2u * (uint32_t)segment, rng.k0 = P.seed_lo, rng.k1 = P.seed_hi;
+        float um[4];
+        rng_next4(rng, um);
+        sample_media(S, r, RTB_T_MIN, um, t, medium);
+    }
+    t_out = t;
+    int mat;
+    if (medium >= 0) {
+        code_out = WF_MEDIUM | medium;
+        mat = (int)as_uint(ld4(reinterpret_cast<const char*>(S.media + medium) + 32).y);
+    } else if (prim >= 0) {
+        code_out = prim | (face << 24);
+        mat = (int)as_uint(ld4(reinterpret_cast<const char*>(S.prims + prim) + 16).w);
+    } else {
+        code_out = -1;
+        return WF_MISS;
+    }
+    float4 m = ld4(S.mats + mat);  // kind, tex, fuzz, ior
+    if ((int)as_uint(m.y) >= 0) return WF_TEXTURED;
+    return (int)as_uint(m.x);  // MAT_* == WF_* for the five material kinds
+}
+
+// the shade stage for one path: scatter or terminate.  Returns true while alive (slot updated in place);
+// otherwise `radiance` is the path's contribution to its pixel.
+RTB_DEV bool wf_shade(const DSceneView& S, const DRenderParams& P, WfSlot& s, V3& radiance) {
+    PathState ps;
+    ps.ray.o = v3(s.A.x, s.A.y, s.A.z), ps.ray.d = v3(s.B.x, s.B.y, s.B.z);
+    ps.beta = v3(s.C.x, s.C.y, s.C.z);
+    uint32_t flags = as_uint(s.B.w);
+    ps.depth = (int)(flags & WF_DEPTH_MASK);
+    int segment = P.max_depth - ps.depth;
+    ps.depth -= 1;  // this segment's ray has been traced
+    ps.origin_prim = -1, ps.origin_face = 0;
+    int code = (int)as_uint(s.D.y);
+    float t = s.D.x;
+    if (code < 0) {
+        radiance = ps.beta * background_color(S, ps.ray);
+        return false;
+    }
+    PathRng rng;
+    rng.pixel = as_uint(s.A.w), rng.sample = as_uint(s.D.w), rng.draw = 2u + 2u * (uint32_t)segment, rng.k0 = P.seed_lo, rng.k1 = P.seed_hi;
+    float us[4];
+    rng_next4(rng, us);
+    Surface sf;
+    V3 term;
+    bool alive;
+    if (code & WF_MEDIUM) {
+        int medium = code & 0xFFFF;
+        const DMaterial& mat = S.mats[(int)as_uint(ld4(reinterpret_cast<const char*>(S.media + medium) + 32).y)];
+        sf.p = ps.ray.o + t * ps.ray.d;
+        sf.n = v3(1.f, 0.f, 0.f), sf.u = 0.f, sf.v = 0.f, sf.front = true;
+        alive = scatter(S, mat, sf, us, ps, -1, 0, term);
+    } else {
+        int prim = code & 0xFFFFFF, face = (code >> 24) & 7;
+        PrimRec Pr = load_prim(S.prims + prim);
+        const DMaterial& mat = S.mats[Pr.mat];
+        bool want_uv = mat.tex >= 0 && texture_needs_uv(S, mat.tex);
+        surface_at(S, Pr, ps.ray, t, face, want_uv, sf);
+        alive = scatter(S, mat, sf, us, ps, prim, face, term);
+    }
+    if (!alive) {
+        radiance = ps.beta * term;
+        return false;
+    }
+    if (ps.depth <= 0) {
+        radiance = v3(0.f, 0.f, 0.f);
+        return false;
+    }
+    s.A = f4(ps.ray.o.x, ps.ray.o.y, ps.ray.o.z, s.A.w);
+    s.B = f4(ps.ray.d.x, ps.ray.d.y, ps.ray.d.z, as_float((uint32_t)ps.depth | ((uint32_t)ps.origin_face << WF_FACE_SHIFT)));
+    s.C = f4(ps.beta.x, ps.beta.y, ps.beta.z, 0.f);
+    s.D.z = as_float((uint32_t)ps.origin_prim);
+    return true;
 }
 
 // ------------------------------------------------------------------ test entry points (rt_intersect_batch etc.)

@@ -13,11 +13,12 @@ namespace rtb {
 
 // ---- BVH node, 32 B.  Children of an inner node are adjacent (left = a, right = a + 1) so one 64-byte
 // fetch brings both child boxes; the box of a node lives in the node itself.
+// `a` is the traversal link: >= 0 = index of the left child of an inner node, < 0 = ~(first | count << 24) of a leaf.
 struct alignas(16) DNode {
     float lo[3];
-    int32_t a;  // inner: index of the left child;   leaf: first primitive
+    int32_t a;  // traversal link (see above)
     float hi[3];
-    int32_t b;  // inner: 0;                         leaf: primitive count (> 0)
+    int32_t b;  // inner: 0;  leaf: primitive count (informational)
 };
 
 enum { PRIM_SPHERE = 0, PRIM_BOX = 1 };

@@ -1,0 +1,63 @@
+// The opaque RtScene of include/rt_b200.h and helpers shared by the CUDA translation units (rt_api.cu, rt_wavefront.cu).
+#pragma once
+#include <cuda_runtime.h>
+
+#include <vector>
+
+#include "flatten.h"
+#include "internal.h"
+#include "rt_types.h"
+
+#define CU_TRY(expr)                                                                                                \
+    do {                                                                                                            \
+        cudaError_t e_ = (expr);                                                                                    \
+        if (e_ != cudaSuccess) return rtb::set_error(RT_ERR_CUDA, "%s failed: %s", #expr, cudaGetErrorString(e_)); \
+    } while (0)
+
+namespace rtb {
+
+struct DeviceGuard {  // run on the scene's device, restore the caller's afterwards
+    int prev = -1;
+    explicit DeviceGuard(int dev) {
+        cudaGetDevice(&prev);
+        if (dev != prev) cudaSetDevice(dev);
+    }
+    ~DeviceGuard() {
+        int cur = -1;
+        cudaGetDevice(&cur);
+        if (prev >= 0 && cur != prev) cudaSetDevice(prev);
+    }
+};
+
+struct WavefrontState;  // rt_wavefront.cu
+
+DRenderParams device_params(const RtParams* p, int first_sample, int spi, int chunks);
+
+}  // namespace rtb
+
+struct RtScene {
+    int device = 0;
+    rtb::DSceneView view{};
+    rtb::FlatScene flat;  // host copy (info + hit -> description node mapping)
+    std::vector<void*> owned;
+    std::vector<cudaArray_t> arrays;
+    std::vector<cudaTextureObject_t> textures;
+    int64_t device_bytes = 0;
+    rtb::OwnedDesc* desc = nullptr;  // deep copy of the description (sub-tree queries of rt_intersect_batch)
+    // scratch of rt_render (host-buffer entry point), grown on demand
+    float* d_accum = nullptr;
+    int32_t* d_rgb = nullptr;
+    size_t scratch_values = 0;
+    unsigned long long* d_rays = nullptr;
+    cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+    rtb::WavefrontState* wf = nullptr;  // path pool + queues of the wavefront pipeline, allocated on first use
+};
+
+namespace rtb {
+// pipelines: samples [begin, begin+count) of every pixel, ADDED into d_accum; *launches counts kernel launches
+int launch_megakernel(const RtScene* s, const DCamera& cam, const RtParams* p, int begin, int count, float* d_accum, cudaStream_t stream,
+                      RtProgressFn cb, void* user, int* launches);
+int launch_wavefront(RtScene* s, const DCamera& cam, const RtParams* p, int begin, int count, float* d_accum, cudaStream_t stream,
+                     RtProgressFn cb, void* user, int* launches);
+void free_wavefront(RtScene* s);
+}  // namespace rtb

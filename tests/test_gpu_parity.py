@@ -72,16 +72,23 @@ def test_closest_hit_matches_oracle(name):
     scene.close()
 
 
+PIPELINES = {"megakernel": abi.RT_PIPELINE_MEGAKERNEL, "wavefront": abi.RT_PIPELINE_WAVEFRONT}
+
+
+@pytest.mark.parametrize("pipeline", list(PIPELINES))
 @pytest.mark.parametrize("name,aspect,spp", [("random", 1.5, 64), ("cornell_smoke", 1.0, 64), ("final_scene", 1.0, 64)])
-def test_image_rmse_within_noise_floor(name, aspect, spp):
+def test_image_rmse_within_noise_floor(name, aspect, spp, pipeline):
     world = rt.World(name)
-    scene = rt.Scene(world.build(42))
+    desc = world.build(42)
+    scene = rt.Scene(desc)
     ow = S.OracleWorld(name, 42)
     cam = S.make_camera(ow.lookfrom, ow.lookat, ow.vfov, aspect)
     W = 120
     H = int(W / aspect)
     r = rt.Renderer.new_with_rng(cam, scene, world.background(), rt.RenderingParams(spp, H, W), rt.RecursiveRayTracer(50), rt.SeedableRngator(42))
+    r.pipeline = PIPELINES[pipeline]
     rgb, accum = r.render_arrays()
+    assert r.stats["pipeline"] == PIPELINES[pipeline]
     a1, rgb1, c1, _ = ow.render(cam.c, W, H, spp, render_seed=42)
     a2, _, _, _ = ow.render(cam.c, W, H, spp, render_seed=977)
     rm = lambda x, y: float(np.sqrt(np.mean((x - y) ** 2)))
@@ -97,4 +104,51 @@ def test_image_rmse_within_noise_floor(name, aspect, spp):
     x = np.sqrt(accum.astype(np.float64) * (1.0 / spp))
     exp = (255.999 * np.clip(x, 0.0, 0.99999999)).astype(np.int32)
     assert np.array_equal(rgb, exp)
+    scene.close()
+
+
+@pytest.mark.parametrize("name,aspect", [("random", 1.5), ("cornell_smoke", 1.0), ("final_scene", 1.0), ("cornell_box", 1.0), ("simple", 16 / 9)])
+def test_wavefront_and_megakernel_agree(name, aspect):
+    """Both pipelines draw the same Philox numbers for the same (pixel, sample, segment), so they trace the SAME
+    paths up to the compiler's different FMA contraction of the shared device functions in the two kernels (a
+    handful of grazing paths take another branch): ray counts agree to 1e-3 and nearly all pixels to float rounding."""
+    world = rt.World(name)
+    desc = world.build(42)
+    scene = rt.Scene(desc)
+    info = world.camera()
+    cam = S.make_camera(info["lookfrom"], info["lookat"], info["field_of_view"], aspect)
+    W, spp = 96, 24
+    H = int(W / aspect)
+    out = {}
+    for pname, pid in PIPELINES.items():
+        r = rt.Renderer.new_with_rng(cam, scene, world.background(), rt.RenderingParams(spp, H, W), rt.RecursiveRayTracer(50), rt.SeedableRngator(7))
+        r.pipeline = pid
+        rgb, accum = r.render_arrays()
+        out[pname] = (rgb, accum.astype(np.float64), r.stats)
+    a, b = out["megakernel"], out["wavefront"]
+    assert a[2]["paths"] == b[2]["paths"] == W * H * spp
+    assert abs(a[2]["rays"] - b[2]["rays"]) <= 1e-3 * a[2]["rays"]
+    close = np.isclose(a[1], b[1], rtol=1e-4, atol=1e-4 * a[1].mean()).all(axis=2)
+    assert close.mean() > 0.98, close.mean()
+    assert abs(a[1].mean() - b[1].mean()) < 2e-3 * a[1].mean()
+    scene.close()
+
+
+def test_wavefront_many_rounds_small_pool(monkeypatch):
+    """a pool much smaller than the job: thousands of regenerations, graph batches and the termination logic"""
+    monkeypatch.setenv("RT_WF_SLOTS", "4096")
+    world = rt.World("cornell_smoke")
+    desc = world.build(0)
+    scene = rt.Scene(desc)
+    info = world.camera()
+    cam = S.make_camera(info["lookfrom"], info["lookat"], info["field_of_view"], 1.0)
+    res = {}
+    for pname, pid in PIPELINES.items():
+        r = rt.Renderer.new_with_rng(cam, scene, world.background(), rt.RenderingParams(16, 64, 64), rt.RecursiveRayTracer(50), rt.SeedableRngator(3))
+        r.pipeline = pid
+        _, accum = r.render_arrays()
+        res[pname] = (accum.astype(np.float64), r.stats)
+    assert abs(res["megakernel"][1]["rays"] - res["wavefront"][1]["rays"]) <= 2e-3 * res["megakernel"][1]["rays"]
+    close = np.isclose(res["megakernel"][0], res["wavefront"][0], rtol=1e-4, atol=1e-3).all(axis=2)
+    assert close.mean() > 0.97, close.mean()
     scene.close()
