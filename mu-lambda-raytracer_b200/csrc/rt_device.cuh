@@ -653,18 +653,21 @@ RTB_DEV bool extend_and_shade(const DSceneView& S, PathState& ps, PathRng& rng, 
         return false;
     }
     ps.depth -= 1;
-    float t;
-    int prim, face;
-    closest_hit(S, ps.ray, RTB_T_MIN, RTB_INF, ps.origin_prim, ps.origin_face, t, prim, face);
+    // Media first: the free-flight event of ConstantMedium::hit (volumes.rs:44-53) does not depend on the surfaces,
+    // only its acceptance does (event before the nearest surface), so the closest event is drawn up front and
+    // bounds the surface search.  Philox draw indices are a function of the segment number k alone (camera = 0,
+    // media = 1 + 2k, scatter = 2 + 2k), so the megakernel and the wavefront pipeline consume identical streams.
+    float t = RTB_INF;
     int medium = -1;
-    // Philox draw indices are a function of the segment number k alone (camera = 0, media = 1 + 2k, scatter =
-    // 2 + 2k), so the megakernel and the wavefront pipeline consume identical streams.
     rng.draw = 1u + 2u * (uint32_t)segment;
     if (S.n_media > 0) {
         float um[4];
         rng_next4(rng, um);
         sample_media(S, ps.ray, RTB_T_MIN, um, t, medium);
     }
+    int prim, face;
+    closest_hit(S, ps.ray, RTB_T_MIN, t, ps.origin_prim, ps.origin_face, t, prim, face);
+    if (prim >= 0) medium = -1;
     rng.draw = 2u + 2u * (uint32_t)segment;
     if (prim < 0 && medium < 0) {
         radiance = ps.beta * background_color(S, ps.ray);
@@ -749,8 +752,10 @@ RTB_DEV void integrate_item(const DSceneView& S, const DCamera& cam, const DRend
 
 // ------------------------------------------------------------------ wavefront path state (rt_wavefront.cu)
 // One pool slot = four 128-bit words:
-//   A = origin.xyz, pixel            B = direction.xyz, flags (depth left | origin face)
-//   C = beta.rgb, -                  D = hit t, hit code, origin primitive, sample index
+//   A = origin.xyz, pixel            B = direction.xyz, flags (depth left | origin face << 16)
+//   C = beta.rgb, sample index       D = t, code, origin primitive, -
+// D.t / D.code enter the extend stage as the pre-sampled medium event (t_max of the surface search; +inf / -1 if
+// none) and leave it as the final hit.
 // hit code: -1 miss, prim | face << 24 for a surface, WF_MEDIUM | m for a medium event.
 enum { WF_MISS = 0, WF_LAMBERTIAN = 1, WF_METAL = 2, WF_DIELECTRIC = 3, WF_LIGHT = 4, WF_ISOTROPIC = 5, WF_TEXTURED = 6, WF_CLASSES = 7 };
 #define WF_MEDIUM 0x40000000
@@ -766,9 +771,27 @@ RTB_DEV float4 f4(float x, float y, float z, float w) {
     return v;
 }
 
+// the closest medium event along the slot's (new) ray, drawn with the media uniforms of segment `segment`; it
+// becomes the t_max (and fallback hit code) of the surface search in the extend stage
+RTB_DEV void wf_presample_media(const DSceneView& S, const DRenderParams& P, WfSlot& s, int segment) {
+    float t = RTB_INF;
+    int medium = -1;
+    if (S.n_media > 0) {
+        Ray r;
+        r.o = v3(s.A.x, s.A.y, s.A.z), r.d = v3(s.B.x, s.B.y, s.B.z);
+        PathRng rng;
+        rng.pixel = as_uint(s.A.w), rng.sample = as_uint(s.C.w), rng.draw = 1u + 2u * (uint32_t)segment, rng.k0 = P.seed_lo, rng.k1 = P.seed_hi;
+        float um[4];
+        rng_next4(rng, um);
+        sample_media(S, r, RTB_T_MIN, um, t, medium);
+    }
+    s.D.x = t;
+    s.D.y = as_float(medium >= 0 ? (uint32_t)(WF_MEDIUM | medium) : 0xFFFFFFFFu);
+}
+
 // a fresh camera path: global path number -> (pixel, sample); sample-major so that consecutive paths are
 // neighbouring pixels of one sample index
-RTB_DEV void wf_init_path(const DCamera& cam, const DRenderParams& P, unsigned long long path, WfSlot& s) {
+RTB_DEV void wf_init_path(const DSceneView& S, const DCamera& cam, const DRenderParams& P, unsigned long long path, WfSlot& s) {
     unsigned long long npix = (unsigned long long)P.width * (unsigned long long)P.height;
     uint32_t sample = (uint32_t)P.sample_begin + (uint32_t)(path / npix);
     uint32_t pixel = (uint32_t)(path % npix);
@@ -779,42 +802,29 @@ RTB_DEV void wf_init_path(const DCamera& cam, const DRenderParams& P, unsigned l
     Ray r = generate_camera_ray(cam, P, (int)(pixel % (uint32_t)P.width), (int)(pixel / (uint32_t)P.width), u);
     s.A = f4(r.o.x, r.o.y, r.o.z, as_float(pixel));
     s.B = f4(r.d.x, r.d.y, r.d.z, as_float((uint32_t)P.max_depth));
-    s.C = f4(1.f, 1.f, 1.f, 0.f);
-    s.D = f4(0.f, as_float(0xFFFFFFFFu), as_float(0xFFFFFFFFu), as_float(sample));
+    s.C = f4(1.f, 1.f, 1.f, as_float(sample));
+    s.D = f4(0.f, 0.f, as_float(0xFFFFFFFFu), 0.f);
+    wf_presample_media(S, P, s, 0);
 }
 
-// end of the extend stage for one ray: media free-flight sampling on top of the surface search, then the queue
-// class the shade stage will pick the path up from.  Returns the class; writes hit t / code.
-RTB_DEV int wf_finish_extend(const DSceneView& S, const DRenderParams& P, const Ray& r, uint32_t pixel, uint32_t sample, uint32_t flags, float t, int prim,
-                             int face, float& t_out, int& code_out) {
-    int medium = -1;
-    if (S.n_media > 0) {
-        int segment = P.max_depth - (int)(flags & WF_DEPTH_MASK);
-        PathRng rng;
-        rng.pixel = pixel, rng.sample = sample, rng.draw = 1u + 2u * (uint32_t)segment, rng.k0 = P.seed_lo, rng.k1 = P.seed_hi;
-        float um[4];
-        rng_next4(rng, um);
-        sample_media(S, r, RTB_T_MIN, um, t, medium);
-    }
-    t_out = t;
-    int mat;
-    if (medium >= 0) {
-        code_out = WF_MEDIUM | medium;
-        mat = (int)as_uint(ld4(reinterpret_cast<const char*>(S.media + medium) + 32).y);
-    } else if (prim >= 0) {
+// end of the extend stage for one ray: final hit code and the queue class the shade stage picks the path up from.
+// prim/face/mat describe the closest surface found below the incoming t_max (prim < 0: none, the incoming code
+// — a medium event or a miss — stands).
+RTB_DEV int wf_classify(const DSceneView& S, int prim, int face, int mat, int code_in, int& code_out) {
+    if (prim >= 0) {
         code_out = prim | (face << 24);
-        mat = (int)as_uint(ld4(reinterpret_cast<const char*>(S.prims + prim) + 16).w);
     } else {
-        code_out = -1;
-        return WF_MISS;
+        code_out = code_in;
+        if (code_in < 0) return WF_MISS;
+        mat = (int)as_uint(ld4(reinterpret_cast<const char*>(S.media + (code_in & 0xFFFF)) + 32).y);
     }
     float4 m = ld4(S.mats + mat);  // kind, tex, fuzz, ior
     if ((int)as_uint(m.y) >= 0) return WF_TEXTURED;
     return (int)as_uint(m.x);  // MAT_* == WF_* for the five material kinds
 }
 
-// the shade stage for one path: scatter or terminate.  Returns true while alive (slot updated in place);
-// otherwise `radiance` is the path's contribution to its pixel.
+// the shade stage for one path: scatter or terminate.  Returns true while alive (slot updated in place, media
+// event of the new ray pre-sampled); otherwise `radiance` is the path's contribution to its pixel.
 RTB_DEV bool wf_shade(const DSceneView& S, const DRenderParams& P, WfSlot& s, V3& radiance) {
     PathState ps;
     ps.ray.o = v3(s.A.x, s.A.y, s.A.z), ps.ray.d = v3(s.B.x, s.B.y, s.B.z);
@@ -831,7 +841,7 @@ RTB_DEV bool wf_shade(const DSceneView& S, const DRenderParams& P, WfSlot& s, V3
         return false;
     }
     PathRng rng;
-    rng.pixel = as_uint(s.A.w), rng.sample = as_uint(s.D.w), rng.draw = 2u + 2u * (uint32_t)segment, rng.k0 = P.seed_lo, rng.k1 = P.seed_hi;
+    rng.pixel = as_uint(s.A.w), rng.sample = as_uint(s.C.w), rng.draw = 2u + 2u * (uint32_t)segment, rng.k0 = P.seed_lo, rng.k1 = P.seed_hi;
     float us[4];
     rng_next4(rng, us);
     Surface sf;
@@ -861,8 +871,9 @@ RTB_DEV bool wf_shade(const DSceneView& S, const DRenderParams& P, WfSlot& s, V3
     }
     s.A = f4(ps.ray.o.x, ps.ray.o.y, ps.ray.o.z, s.A.w);
     s.B = f4(ps.ray.d.x, ps.ray.d.y, ps.ray.d.z, as_float((uint32_t)ps.depth | ((uint32_t)ps.origin_face << WF_FACE_SHIFT)));
-    s.C = f4(ps.beta.x, ps.beta.y, ps.beta.z, 0.f);
+    s.C = f4(ps.beta.x, ps.beta.y, ps.beta.z, s.C.w);
     s.D.z = as_float((uint32_t)ps.origin_prim);
+    wf_presample_media(S, P, s, segment + 1);
     return true;
 }
 

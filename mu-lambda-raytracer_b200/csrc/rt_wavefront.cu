@@ -40,8 +40,8 @@ struct WfJob {
 };
 
 struct WfView {
-    float4 *A, *B, *C, *D;  // path pool, n_slots each
-    unsigned int* q[2];     // active queues
+    WfSlot* slots;          // path pool: n_slots records of 64 B (AoS: a path is two full 32-byte sectors)
+    unsigned int* q[2];     // active queues (slot indices)
     unsigned int* cq;       // WF_CLASSES class queues of n_slots entries each
     WfCounters* ctr;
     WfJob* job;
@@ -58,9 +58,17 @@ struct WavefrontState {
 };
 
 #define WF_EXT_THREADS 128
+#define WF_EXT_WARPS (WF_EXT_THREADS / 32)
 #define WF_SHADE_THREADS 256
 #define WF_DONE ((int)0x80000000)
-#define WF_REFILL 8  // lanes that must be idle before a warp stops traversing to retire / fetch rays
+#define WF_REFILL 8       // lanes that must be idle before a warp stops traversing to retire / fetch rays
+#define WF_MIN_DESCEND 8  // lanes that must still be descending inner nodes for the inner loop to keep going
+#define WF_CHUNK 64       // queue entries a warp reserves per atomic
+#define WF_BIN 64         // per-warp, per-class staging entries (flushed 32 at a time)
+
+// streaming accesses for the path pool: it is touched once per round, keep L1 for the BVH
+__device__ __forceinline__ float4 ld_stream(const float4* p) { return __ldcs(p); }
+__device__ __forceinline__ void st_stream(float4* p, float4 v) { __stcs(p, v); }
 
 // ---------------------------------------------------------------------------------------------------------------
 __global__ void wf_reset_kernel(WfView W, unsigned int n_init, unsigned long long total, DCamera cam, DRenderParams P, float* accum) {
@@ -72,138 +80,171 @@ __global__ void wf_reset_kernel(WfView W, unsigned int n_init, unsigned long lon
     c->next_path = n_init, c->total_paths = total, c->rays = 0;
 }
 
-__global__ void wf_init_kernel(WfView W, DCamera cam, DRenderParams P, unsigned int n_init) {
+__global__ void wf_init_kernel(DSceneView S, WfView W, DCamera cam, DRenderParams P, unsigned int n_init) {
     unsigned int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n_init) return;
     WfSlot s;
-    wf_init_path(cam, P, i, s);
-    W.A[i] = s.A, W.B[i] = s.B, W.C[i] = s.C, W.D[i] = s.D;
+    wf_init_path(S, cam, P, i, s);
+    W.slots[i] = s;
     W.q[0][i] = i;
 }
 
 // ---------------------------------------------------------------------------------------------------------------
+// Extend: persistent warps.  Each lane owns one ray at a time; the warp alternates between an inner-node loop
+// (lanes drop out as they reach a leaf; the loop ends when fewer than WF_MIN_DESCEND lanes are still descending)
+// and a leaf step, and retires / refills lanes in batches of at least WF_REFILL.
 __global__ void __launch_bounds__(WF_EXT_THREADS) wf_extend_kernel(DSceneView S, WfView W, int parity) {
+    __shared__ unsigned int bins[WF_EXT_WARPS][WF_CLASSES][WF_BIN];
+    __shared__ unsigned int bin_count[WF_EXT_WARPS][WF_CLASSES + 1];
     WfCounters* ctr = W.ctr;
-    const DRenderParams P = W.job->P;
     const unsigned int qn = ctr->q_count[parity];
     const unsigned int* __restrict__ Q = W.q[parity];
-    const unsigned int lane = threadIdx.x & 31u;
+    const unsigned int lane = threadIdx.x & 31u, warp = threadIdx.x >> 5;
     const unsigned int lt_mask = (1u << lane) - 1u;
+    if (lane <= WF_CLASSES) bin_count[warp][lane] = 0;
+    __syncwarp();
 
     int stack[RTB_BVH_STACK];
     int sp = 0;
     int cur = WF_DONE;
     bool has = false;
     bool exhausted = qn == 0;
-    unsigned int slot = 0, pixel = 0, sample = 0, flags = 0;
+    unsigned int chunk_next = 0, chunk_end = 0;  // this warp's reserved range of queue positions
+    unsigned int slot = 0, flags = 0;
     Ray r;
     r.o = r.d = v3(0.f, 0.f, 0.f);
     V3 inv = v3(0.f, 0.f, 0.f);
     float t_best = RTB_INF;
-    int prim_best = -1, face_best = 0, origin_prim = -1;
+    int prim_best = -1, face_best = 0, mat_best = 0, origin_prim = -1, code_in = -1;
     const int root_link = S.n_prims > 0 ? (int)as_uint(ld4(S.nodes).w) : WF_DONE;
 
     for (;;) {
-        // ---- retire finished rays in batches: media sample, hit record, class queue
         bool fin = has && cur == WF_DONE;
         unsigned int fin_mask = __ballot_sync(0xffffffffu, fin);
         unsigned int trav_mask = __ballot_sync(0xffffffffu, has && cur != WF_DONE);
         unsigned int empty_mask = __ballot_sync(0xffffffffu, !has);
+        // ---- retire finished rays in batches: hit record + class bin (staged in shared memory, flushed by 32)
         if (fin_mask && (__popc(fin_mask | empty_mask) >= WF_REFILL || trav_mask == 0u)) {
             int cls = -1;
             if (fin) {
-                float t_out;
                 int code;
-                cls = wf_finish_extend(S, P, r, pixel, sample, flags, t_best, prim_best, face_best, t_out, code);
+                cls = wf_classify(S, prim_best, face_best, mat_best, code_in, code);
                 float2 rec;
-                rec.x = t_out, rec.y = __int_as_float(code);
-                *reinterpret_cast<float2*>(&W.D[slot]) = rec;
+                rec.x = t_best, rec.y = __int_as_float(code);
+                *reinterpret_cast<float2*>(&W.slots[slot].D) = rec;
             }
 #pragma unroll
             for (int c = 0; c < WF_CLASSES; ++c) {
                 unsigned int m = __ballot_sync(0xffffffffu, cls == c);
                 if (m) {
-                    unsigned int base = 0;
-                    int leader = __ffs(m) - 1;
-                    if ((int)lane == leader) base = atomicAdd(&ctr->class_count[c], (unsigned int)__popc(m));
-                    base = __shfl_sync(0xffffffffu, base, leader);
-                    if (cls == c) W.cq[(size_t)c * W.n_slots + base + __popc(m & lt_mask)] = slot;
+                    unsigned int n0 = bin_count[warp][c];
+                    if (cls == c) bins[warp][c][n0 + __popc(m & lt_mask)] = slot;
+                    unsigned int n1 = n0 + (unsigned int)__popc(m);
+                    __syncwarp();
+                    if (n1 >= 32u) {  // flush one full, coalesced line of slot indices
+                        unsigned int base = 0;
+                        if (lane == 0) base = atomicAdd(&ctr->class_count[c], 32u);
+                        base = __shfl_sync(0xffffffffu, base, 0);
+                        W.cq[(size_t)c * W.n_slots + base + lane] = bins[warp][c][lane];
+                        unsigned int keep = lane + 32u < n1 ? bins[warp][c][lane + 32u] : 0u;
+                        __syncwarp();
+                        bins[warp][c][lane] = keep;
+                        n1 -= 32u;
+                    }
+                    __syncwarp();
+                    if (lane == 0) bin_count[warp][c] = n1;
+                    __syncwarp();
                 }
             }
             if (fin) has = false;
             empty_mask |= fin_mask;
         }
-        // ---- refill empty lanes from the active queue: one atomic per warp
+        // ---- refill empty lanes from this warp's chunk of the active queue (one atomic per WF_CHUNK rays)
         if (!exhausted && empty_mask && (__popc(empty_mask) >= WF_REFILL || trav_mask == 0u)) {
-            unsigned int n = (unsigned int)__popc(empty_mask);
-            unsigned int base = 0;
-            if (lane == 0) base = atomicAdd(&ctr->q_head, n);
-            base = __shfl_sync(0xffffffffu, base, 0);
-            if (!has) {
-                unsigned int my = base + (unsigned int)__popc(empty_mask & lt_mask);
-                if (my < qn) {
-                    slot = Q[my];
-                    float4 a = W.A[slot], b = W.B[slot], d = W.D[slot];
-                    r.o = v3(a.x, a.y, a.z), r.d = v3(b.x, b.y, b.z);
-                    pixel = __float_as_uint(a.w), flags = __float_as_uint(b.w), sample = __float_as_uint(d.w);
-                    origin_prim = (int)__float_as_uint(d.z);
-                    inv = v3(1.0f / r.d.x, 1.0f / r.d.y, 1.0f / r.d.z);
-                    t_best = RTB_INF, prim_best = -1, face_best = 0;
-                    sp = 0, cur = root_link;
-                    has = true;
-                }
+            if (chunk_next == chunk_end) {
+                unsigned int base = 0;
+                if (lane == 0) base = atomicAdd(&ctr->q_head, (unsigned int)WF_CHUNK);
+                base = __shfl_sync(0xffffffffu, base, 0);
+                chunk_next = min(base, qn), chunk_end = min(base + (unsigned int)WF_CHUNK, qn);
+                if (chunk_next == chunk_end) exhausted = true;
             }
-            if (base + n >= qn) exhausted = true;
+            unsigned int my = chunk_next + (unsigned int)__popc(empty_mask & lt_mask);
+            if (!has && my < chunk_end) {
+                slot = Q[my];
+                const float4* rec = reinterpret_cast<const float4*>(W.slots + slot);
+                float4 a = ld_stream(rec), b = ld_stream(rec + 1), d = ld_stream(rec + 3);
+                r.o = v3(a.x, a.y, a.z), r.d = v3(b.x, b.y, b.z);
+                flags = __float_as_uint(b.w);
+                t_best = d.x, code_in = __float_as_int(d.y), origin_prim = __float_as_int(d.z);
+                inv = v3(1.0f / r.d.x, 1.0f / r.d.y, 1.0f / r.d.z);
+                prim_best = -1, face_best = 0;
+                sp = 0, cur = root_link;
+                has = true;
+            }
+            chunk_next = min(chunk_next + (unsigned int)__popc(empty_mask), chunk_end);
         }
-        if (__ballot_sync(0xffffffffu, has) == 0u) break;  // nothing in flight and the queue is empty
+        if (__ballot_sync(0xffffffffu, has) == 0u) {
+            if (exhausted) break;
+            continue;  // chunk ran dry mid-refill: fetch the next one
+        }
 
-        // ---- traversal: the warp votes between "one inner-node step" and "one leaf-primitive step"
+        // ---- traversal
         for (;;) {
-            bool inner = has && cur >= 0;
-            bool leaf = has && cur < 0 && cur != WF_DONE;
-            unsigned int mi = __ballot_sync(0xffffffffu, inner), ml = __ballot_sync(0xffffffffu, leaf);
-            if ((mi | ml) == 0u) break;
-            if (__popc(mi) >= __popc(ml)) {
-                if (inner) {
-                    const char* base = reinterpret_cast<const char*>(S.nodes + cur);
-                    float4 l0 = ld4(base), l1 = ld4(base + 16), r0 = ld4(base + 32), r1 = ld4(base + 48);
-                    float tl, tr;
-                    bool hl = slab_node(l0, l1, r.o, inv, RTB_T_MIN, t_best, tl);
-                    bool hr = slab_node(r0, r1, r.o, inv, RTB_T_MIN, t_best, tr);
-                    int ll = (int)as_uint(l0.w), lr = (int)as_uint(r0.w);
-                    if (hl && hr) {
-                        bool left_first = tl <= tr;
-                        stack[sp++] = left_first ? lr : ll;
-                        cur = left_first ? ll : lr;
-                    } else if (hl) {
-                        cur = ll;
-                    } else if (hr) {
-                        cur = lr;
-                    } else {
-                        cur = sp > 0 ? stack[--sp] : WF_DONE;
-                    }
+            // (a) inner nodes: lanes leave the loop when they reach a leaf or run out of nodes
+            while (has && cur >= 0) {
+                const char* base = reinterpret_cast<const char*>(S.nodes + cur);
+                float4 l0 = ld4(base), l1 = ld4(base + 16), r0 = ld4(base + 32), r1 = ld4(base + 48);
+                float tl, tr;
+                bool hl = slab_node(l0, l1, r.o, inv, RTB_T_MIN, t_best, tl);
+                bool hr = slab_node(r0, r1, r.o, inv, RTB_T_MIN, t_best, tr);
+                int ll = (int)as_uint(l0.w), lr = (int)as_uint(r0.w);
+                if (hl && hr) {
+                    bool left_first = tl <= tr;
+                    stack[sp++] = left_first ? lr : ll;
+                    cur = left_first ? ll : lr;
+                } else if (hl) {
+                    cur = ll;
+                } else if (hr) {
+                    cur = lr;
+                } else {
+                    cur = sp > 0 ? stack[--sp] : WF_DONE;
                 }
-            } else {
-                if (leaf) {
-                    int v = ~cur;
-                    int first = v & 0xFFFFFF, count = v >> 24;
-                    PrimRec p = load_prim(S.prims + first);
+                if (__popc(__activemask()) < WF_MIN_DESCEND) break;  // too few lanes descending: let the others catch up
+            }
+            __syncwarp();
+            // (b) one leaf: every primitive of it, then pop
+            if (has && cur < 0 && cur != WF_DONE) {
+                int v = ~cur;
+                int first = v & 0xFFFFFF, count = v >> 24;
+                for (int i = first; i < first + count; ++i) {
+                    PrimRec p = load_prim(S.prims + i);
                     float t;
                     int face;
-                    if (hit_prim(S, p, r, RTB_T_MIN, t_best, first == origin_prim, (int)((flags >> WF_FACE_SHIFT) & 7u), t, face))
-                        t_best = t, prim_best = first, face_best = face;
-                    if (count > 1) cur = ~((first + 1) | ((count - 1) << 24));
-                    else cur = sp > 0 ? stack[--sp] : WF_DONE;
+                    if (hit_prim(S, p, r, RTB_T_MIN, t_best, i == origin_prim, (int)((flags >> WF_FACE_SHIFT) & 7u), t, face))
+                        t_best = t, prim_best = i, face_best = face, mat_best = p.mat;
                 }
+                cur = sp > 0 ? stack[--sp] : WF_DONE;
             }
-            if (!exhausted) {
-                unsigned int idle = __ballot_sync(0xffffffffu, !has || cur == WF_DONE);
-                if (__popc(idle) >= WF_REFILL) break;
-            }
+            __syncwarp();
+            // (c) leave for retire/refill when enough lanes are idle, or when nothing is left to traverse
+            unsigned int busy = __ballot_sync(0xffffffffu, has && cur != WF_DONE);
+            if (busy == 0u) break;
+            if (!exhausted && 32 - __popc(busy) >= WF_REFILL) break;
         }
     }
 
-    // ---- last block out: account the rays of this round and rewind the cursors the shade stage does not own
+    // ---- flush the partially filled class bins
+#pragma unroll
+    for (int c = 0; c < WF_CLASSES; ++c) {
+        unsigned int n = bin_count[warp][c];
+        if (n) {
+            unsigned int base = 0;
+            if (lane == 0) base = atomicAdd(&ctr->class_count[c], n);
+            base = __shfl_sync(0xffffffffu, base, 0);
+            if (lane < n) W.cq[(size_t)c * W.n_slots + base + lane] = bins[warp][c][lane];
+        }
+    }
+    // ---- last block out: account the rays of this round and rewind the fetch cursor
     __syncthreads();
     if (threadIdx.x == 0) {
         __threadfence();
@@ -219,11 +260,33 @@ __global__ void __launch_bounds__(WF_EXT_THREADS) wf_extend_kernel(DSceneView S,
 }
 
 // ---------------------------------------------------------------------------------------------------------------
+// block-wide exclusive rank of the threads with `flag` set; returns the block total in `total`
+__device__ __forceinline__ unsigned int block_rank(bool flag, unsigned int* warp_sums, unsigned int& total) {
+    const unsigned int lane = threadIdx.x & 31u, warp = threadIdx.x >> 5;
+    unsigned int m = __ballot_sync(0xffffffffu, flag);
+    if (lane == 0) warp_sums[warp] = (unsigned int)__popc(m);
+    __syncthreads();
+    unsigned int before = 0, all = 0;
+#pragma unroll
+    for (unsigned int w = 0; w < WF_SHADE_THREADS / 32; ++w) {
+        unsigned int v = warp_sums[w];
+        before += w < warp ? v : 0u;
+        all += v;
+    }
+    __syncthreads();
+    total = all;
+    return before + (unsigned int)__popc(m & ((1u << lane) - 1u));
+}
+
+// Shade: one thread per queued path; blocks are class-uniform.  Two atomics per BLOCK: one reserves camera-path
+// numbers for the regenerated paths, one reserves the block's range of the next active queue.
 __global__ void __launch_bounds__(WF_SHADE_THREADS) wf_shade_kernel(DSceneView S, WfView W, int parity) {
+    __shared__ unsigned int warp_sums[WF_SHADE_THREADS / 32];
+    __shared__ unsigned long long path_base;
+    __shared__ unsigned int queue_base;
     WfCounters* ctr = W.ctr;
     const DRenderParams P = W.job->P;
     float* __restrict__ accum = W.job->accum;
-    // blocks are class-uniform: block b belongs to the class whose block range contains it
     int cls = -1;
     unsigned int item = 0, n_in_class = 0;
     {
@@ -240,51 +303,49 @@ __global__ void __launch_bounds__(WF_SHADE_THREADS) wf_shade_kernel(DSceneView S
             start += nb;
         }
     }
-    const unsigned int lane = threadIdx.x & 31u;
-    const unsigned int lt_mask = (1u << lane) - 1u;
-    unsigned int* __restrict__ Qout = W.q[parity ^ 1];
-    bool valid = cls >= 0 && item < n_in_class;
     if (cls >= 0) {  // uniform per block
+        unsigned int* __restrict__ Qout = W.q[parity ^ 1];
+        bool valid = item < n_in_class;
         unsigned int slot = 0;
         WfSlot s;
         bool alive = false, dead = false;
         V3 radiance = v3(0.f, 0.f, 0.f);
         if (valid) {
             slot = W.cq[(size_t)cls * W.n_slots + item];
-            s.A = W.A[slot], s.B = W.B[slot], s.C = W.C[slot], s.D = W.D[slot];
+            const float4* rec = reinterpret_cast<const float4*>(W.slots + slot);
+            s.A = ld_stream(rec), s.B = ld_stream(rec + 1), s.C = ld_stream(rec + 2), s.D = ld_stream(rec + 3);
             alive = wf_shade(S, P, s, radiance);
             dead = !alive;
         }
         // terminated paths: deposit, then regenerate in place while camera paths remain
-        unsigned int dead_mask = __ballot_sync(0xffffffffu, dead);
-        if (dead_mask) {
-            unsigned long long base = 0;
-            int leader = __ffs(dead_mask) - 1;
-            if ((int)lane == leader) base = atomicAdd(&ctr->next_path, (unsigned long long)__popc(dead_mask));
-            base = __shfl_sync(0xffffffffu, base, leader);
+        unsigned int n_dead;
+        unsigned int dead_rank = block_rank(dead, warp_sums, n_dead);
+        if (n_dead) {
+            if (threadIdx.x == 0) path_base = atomicAdd(&ctr->next_path, (unsigned long long)n_dead);
+            __syncthreads();
             if (dead) {
                 unsigned int pixel = __float_as_uint(s.A.w);
                 float* dst = accum + 3 * (size_t)pixel;
                 if (radiance.x != 0.f) atomicAdd(dst + 0, radiance.x);
                 if (radiance.y != 0.f) atomicAdd(dst + 1, radiance.y);
                 if (radiance.z != 0.f) atomicAdd(dst + 2, radiance.z);
-                unsigned long long path = base + (unsigned long long)__popc(dead_mask & lt_mask);
+                unsigned long long path = path_base + dead_rank;
                 if (path < ctr->total_paths) {
-                    wf_init_path(W.job->cam, P, path, s);
+                    wf_init_path(S, W.job->cam, P, path, s);
                     alive = true;
                 }
             }
         }
-        // survivors (scattered or regenerated) -> next active queue, compacted with ballot ranks
-        unsigned int alive_mask = __ballot_sync(0xffffffffu, alive);
-        if (alive_mask) {
-            unsigned int base = 0;
-            int leader = __ffs(alive_mask) - 1;
-            if ((int)lane == leader) base = atomicAdd(&ctr->q_count[parity ^ 1], (unsigned int)__popc(alive_mask));
-            base = __shfl_sync(0xffffffffu, base, leader);
+        // survivors (scattered or regenerated) -> next active queue
+        unsigned int n_alive;
+        unsigned int alive_rank = block_rank(alive, warp_sums, n_alive);
+        if (n_alive) {
+            if (threadIdx.x == 0) queue_base = atomicAdd(&ctr->q_count[parity ^ 1], n_alive);
+            __syncthreads();
             if (alive) {
-                W.A[slot] = s.A, W.B[slot] = s.B, W.C[slot] = s.C, W.D[slot] = s.D;
-                Qout[base + __popc(alive_mask & lt_mask)] = slot;
+                float4* rec = reinterpret_cast<float4*>(W.slots + slot);
+                st_stream(rec, s.A), st_stream(rec + 1, s.B), st_stream(rec + 2, s.C), st_stream(rec + 3, s.D);
+                Qout[queue_base + alive_rank] = slot;
             }
         }
     }
@@ -320,8 +381,7 @@ int ensure_state(RtScene* s, unsigned int n_slots) {
     WavefrontState* w = new WavefrontState();
     s->wf = w;
     int rc;
-    if ((rc = wf_alloc(w, &w->view.A, n_slots)) || (rc = wf_alloc(w, &w->view.B, n_slots)) || (rc = wf_alloc(w, &w->view.C, n_slots)) ||
-        (rc = wf_alloc(w, &w->view.D, n_slots)) || (rc = wf_alloc(w, &w->view.q[0], n_slots)) || (rc = wf_alloc(w, &w->view.q[1], n_slots)) ||
+    if ((rc = wf_alloc(w, &w->view.slots, n_slots)) || (rc = wf_alloc(w, &w->view.q[0], n_slots)) || (rc = wf_alloc(w, &w->view.q[1], n_slots)) ||
         (rc = wf_alloc(w, &w->view.cq, (size_t)n_slots * WF_CLASSES)) || (rc = wf_alloc(w, &w->view.ctr, 1)) || (rc = wf_alloc(w, &w->view.job, 1)))
         return rc;
     w->view.n_slots = n_slots;
@@ -359,7 +419,7 @@ int launch_wavefront(RtScene* s, const DCamera& cam, const RtParams* p, int begi
     if (p->max_depth <= 0) return RT_OK;  // every path returns Color::ZERO at once (raytrace.rs:87-89)
     if (s->flat.prims.size() >= (1u << 24)) return set_error(RT_ERR_UNSUPPORTED, "wavefront pipeline: more than 2^24 primitives");
     unsigned long long total = (unsigned long long)p->width * p->height * (unsigned long long)count;
-    unsigned int n_slots = 1u << 20;
+    unsigned int n_slots = 1u << 19;
     if (const char* e = getenv("RT_WF_SLOTS")) n_slots = std::max(1024u, (unsigned int)strtoul(e, nullptr, 10));
     int rc = ensure_state(s, n_slots);
     if (rc != RT_OK) return rc;
@@ -368,7 +428,7 @@ int launch_wavefront(RtScene* s, const DCamera& cam, const RtParams* p, int begi
     unsigned int n_init = (unsigned int)std::min<unsigned long long>(total, n_slots);
 
     wf_reset_kernel<<<1, 1, 0, stream>>>(w->view, n_init, total, cam, P, d_accum);
-    wf_init_kernel<<<(n_init + 255) / 256, 256, 0, stream>>>(w->view, cam, P, n_init);
+    wf_init_kernel<<<(n_init + 255) / 256, 256, 0, stream>>>(s->view, w->view, cam, P, n_init);
     CU_TRY(cudaGetLastError());
     *launches += 2;
 
