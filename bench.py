@@ -157,7 +157,8 @@ def run_b200(args):
 
     spp = args.spp
     total_spp = spp * world_size  # the image every step produces has spp samples from each GPU
-    pipeline = {"auto": abi.RT_PIPELINE_AUTO, "megakernel": abi.RT_PIPELINE_MEGAKERNEL, "wavefront": abi.RT_PIPELINE_WAVEFRONT}[args.pipeline]
+    pipeline = {"auto": abi.RT_PIPELINE_AUTO, "megakernel": abi.RT_PIPELINE_MEGAKERNEL, "wavefront": abi.RT_PIPELINE_WAVEFRONT,
+                "wavefront_smem": abi.RT_PIPELINE_WAVEFRONT_SMEM}[args.pipeline]
 
     def params(step):
         p = abi.RtParams()
@@ -302,7 +303,7 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--spp", type=int, default=1000, help="samples per pixel per step per GPU")
-    ap.add_argument("--pipeline", default="auto", choices=["auto", "megakernel", "wavefront"])
+    ap.add_argument("--pipeline", default="auto", choices=["auto", "megakernel", "wavefront", "wavefront_smem"])
     ap.add_argument("--samples-per-item", type=int, default=0)
     ap.add_argument("--e2e-steps", type=int, default=2)
     ap.add_argument("--cpu-spp", type=int, default=8, help="spp of the bounded CPU-baseline sample (0 = skip)")

@@ -28,7 +28,7 @@
 
 #if defined(__CUDACC__) && !defined(RTB_HOST_EMULATION)
 #define RTB_DEV __device__ __forceinline__
-#define RTB_DEV_NOINLINE __device__ __noinline__
+#define RTB_DEV_NOINLINE static __device__ __noinline__
 namespace rtb {
 RTB_DEV float4 ld4(const void* p) { return __ldg(reinterpret_cast<const float4*>(p)); }
 RTB_DEV uint32_t mulhi32(uint32_t a, uint32_t b) { return __umulhi(a, b); }
@@ -190,41 +190,53 @@ RTB_DEV int prim_instance(const PrimRec& p) { return (int)((p.meta >> PRIM_INST_
 
 // Sphere::hit (shapes.rs:57-82).  `from_surface`: the ray starts on this very sphere, so one root is
 // analytically zero (the reference rejects it through t_min) and the other is -2*half_b/a.
+// f32 loses the quadratic's constant term c = |oc|^2 - r^2 only when the origin sits close to the surface of a
+// large sphere (|c| << r^2); those cases (the r = 1000 ground of `random` seen from just above it) take the f64 path.
+RTB_DEV bool sphere_needs_f64(const PrimRec& p, float c) { return (p.meta & PRIM_BIG) && fabsf(c) < 0.05f * p.v3 * p.v3; }
+
+RTB_DEV void sphere_roots_f64(const DSceneView& S, const PrimRec& p, const Ray& r, bool& real, float& t0, float& t1) {
+    const DBigSphere& b = S.big[as_uint(p.v4)];
+    double ocx = (double)r.o.x - b.c[0], ocy = (double)r.o.y - b.c[1], ocz = (double)r.o.z - b.c[2];
+    double dx = r.d.x, dy = r.d.y, dz = r.d.z;
+    double a = dx * dx + dy * dy + dz * dz;
+    double hb = ocx * dx + ocy * dy + ocz * dz;
+    double c = ocx * ocx + ocy * ocy + ocz * ocz - b.r * b.r;
+    double disc = hb * hb - a * c;
+    real = !(disc < 0.0);
+    double sq = sqrt(real ? disc : 0.0);
+    t0 = (float)((-hb - sq) / a), t1 = (float)((-hb + sq) / a);
+}
+
+// both roots of the sphere quadratic, t0 <= t1 (shapes.rs:57-68); false when the discriminant is negative
+RTB_DEV bool sphere_roots(const DSceneView& S, const PrimRec& p, const Ray& r, float& t0, float& t1) {
+    V3 oc = r.o - v3(p.v0, p.v1, p.v2);
+    float a = dot(r.d, r.d), hb = dot(oc, r.d), inv_a = 1.0f / a;
+    float c = dot(oc, oc) - p.v3 * p.v3;
+    if (sphere_needs_f64(p, c)) {
+        bool real;
+        sphere_roots_f64(S, p, r, real, t0, t1);
+        return real;
+    }
+    // discriminant from the perpendicular offset |oc - (hb/a) d|^2: no cancellation for distant origins
+    V3 l = oc - (hb * inv_a) * r.d;
+    float disc_a = p.v3 * p.v3 - dot(l, l);
+    if (disc_a < 0.0f) return false;
+    float sq = sqrtf(a * disc_a);
+    float q = -(hb + copysignf(sq, hb));
+    float ta = q * inv_a, tb = c / q;
+    t0 = fminf(ta, tb), t1 = fmaxf(ta, tb);
+    return true;
+}
+
+// Sphere::hit (shapes.rs:57-82).  `from_surface`: the ray starts on this very sphere, so one root is
+// analytically zero (the reference rejects it through t_min) and the other is -2*half_b/a.
 RTB_DEV bool hit_sphere(const DSceneView& S, const PrimRec& p, const Ray& r, float tmin, float tmax, bool from_surface, float& t_out) {
     float t0, t1;
-    if (p.meta & PRIM_BIG) {
-        const DBigSphere& b = S.big[as_uint(p.v4)];
-        double ocx = (double)r.o.x - b.c[0], ocy = (double)r.o.y - b.c[1], ocz = (double)r.o.z - b.c[2];
-        double dx = r.d.x, dy = r.d.y, dz = r.d.z;
-        double a = dx * dx + dy * dy + dz * dz;
-        double hb = ocx * dx + ocy * dy + ocz * dz;
-        if (from_surface) {
-            t0 = t1 = (float)(-2.0 * hb / a);
-        } else {
-            double c = ocx * ocx + ocy * ocy + ocz * ocz - b.r * b.r;
-            double disc = hb * hb - a * c;
-            if (disc < 0.0) return false;
-            double sq = sqrt(disc);
-            t0 = (float)((-hb - sq) / a), t1 = (float)((-hb + sq) / a);
-        }
-    } else {
+    if (from_surface) {
         V3 oc = r.o - v3(p.v0, p.v1, p.v2);
-        float a = dot(r.d, r.d);
-        float hb = dot(oc, r.d);
-        float inv_a = 1.0f / a;
-        if (from_surface) {
-            t0 = t1 = -2.0f * hb * inv_a;
-        } else {
-            // discriminant from the perpendicular offset |oc - (hb/a) d|^2: no cancellation for distant origins
-            V3 l = oc - (hb * inv_a) * r.d;
-            float disc_a = p.v3 * p.v3 - dot(l, l);
-            if (disc_a < 0.0f) return false;
-            float sq = sqrtf(a * disc_a);
-            float q = -(hb + copysignf(sq, hb));
-            float c = dot(oc, oc) - p.v3 * p.v3;
-            float ta = q * inv_a, tb = c / q;
-            t0 = fminf(ta, tb), t1 = fmaxf(ta, tb);
-        }
+        t0 = t1 = -2.0f * dot(oc, r.d) / dot(r.d, r.d);
+    } else if (!sphere_roots(S, p, r, t0, t1)) {
+        return false;
     }
     if (t0 >= tmin && t0 <= tmax) {
         t_out = t0;
@@ -239,29 +251,7 @@ RTB_DEV bool hit_sphere(const DSceneView& S, const PrimRec& p, const Ray& r, flo
 
 // both crossings of a sphere boundary over (-inf, +inf): what ConstantMedium asks of its boundary
 RTB_DEV bool sphere_interval(const DSceneView& S, const PrimRec& p, const Ray& r, float& t0, float& t1) {
-    if (p.meta & PRIM_BIG) {
-        const DBigSphere& b = S.big[as_uint(p.v4)];
-        double ocx = (double)r.o.x - b.c[0], ocy = (double)r.o.y - b.c[1], ocz = (double)r.o.z - b.c[2];
-        double dx = r.d.x, dy = r.d.y, dz = r.d.z;
-        double a = dx * dx + dy * dy + dz * dz;
-        double hb = ocx * dx + ocy * dy + ocz * dz;
-        double c = ocx * ocx + ocy * ocy + ocz * ocz - b.r * b.r;
-        double disc = hb * hb - a * c;
-        if (disc < 0.0) return false;
-        double sq = sqrt(disc);
-        t0 = (float)((-hb - sq) / a), t1 = (float)((-hb + sq) / a);
-        return true;
-    }
-    V3 oc = r.o - v3(p.v0, p.v1, p.v2);
-    float a = dot(r.d, r.d), hb = dot(oc, r.d), inv_a = 1.0f / a;
-    V3 l = oc - (hb * inv_a) * r.d;
-    float disc_a = p.v3 * p.v3 - dot(l, l);
-    if (disc_a < 0.0f) return false;
-    float sq = sqrtf(a * disc_a);
-    float q = -(hb + copysignf(sq, hb));
-    float c = dot(oc, oc) - p.v3 * p.v3;
-    float ta = q * inv_a, tb = c / q;
-    t0 = fminf(ta, tb), t1 = fmaxf(ta, tb);
+    if (!sphere_roots(S, p, r, t0, t1)) return false;
     return t0 == t0 && t1 == t1;
 }
 
@@ -789,12 +779,17 @@ RTB_DEV void wf_presample_media(const DSceneView& S, const DRenderParams& P, WfS
     s.D.y = as_float(medium >= 0 ? (uint32_t)(WF_MEDIUM | medium) : 0xFFFFFFFFu);
 }
 
+// a fresh camera path for (pixel, sample)
+RTB_DEV void wf_init_pixel_sample(const DSceneView& S, const DCamera& cam, const DRenderParams& P, uint32_t pixel, uint32_t sample, WfSlot& s);
+
 // a fresh camera path: global path number -> (pixel, sample); sample-major so that consecutive paths are
 // neighbouring pixels of one sample index
 RTB_DEV void wf_init_path(const DSceneView& S, const DCamera& cam, const DRenderParams& P, unsigned long long path, WfSlot& s) {
     unsigned long long npix = (unsigned long long)P.width * (unsigned long long)P.height;
-    uint32_t sample = (uint32_t)P.sample_begin + (uint32_t)(path / npix);
-    uint32_t pixel = (uint32_t)(path % npix);
+    wf_init_pixel_sample(S, cam, P, (uint32_t)(path % npix), (uint32_t)P.sample_begin + (uint32_t)(path / npix), s);
+}
+
+RTB_DEV void wf_init_pixel_sample(const DSceneView& S, const DCamera& cam, const DRenderParams& P, uint32_t pixel, uint32_t sample, WfSlot& s) {
     PathRng rng;
     rng.pixel = pixel, rng.sample = sample, rng.draw = 0, rng.k0 = P.seed_lo, rng.k1 = P.seed_hi;
     float u[4];

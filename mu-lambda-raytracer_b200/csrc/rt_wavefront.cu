@@ -419,7 +419,7 @@ int launch_wavefront(RtScene* s, const DCamera& cam, const RtParams* p, int begi
     if (p->max_depth <= 0) return RT_OK;  // every path returns Color::ZERO at once (raytrace.rs:87-89)
     if (s->flat.prims.size() >= (1u << 24)) return set_error(RT_ERR_UNSUPPORTED, "wavefront pipeline: more than 2^24 primitives");
     unsigned long long total = (unsigned long long)p->width * p->height * (unsigned long long)count;
-    unsigned int n_slots = 1u << 19;
+    unsigned int n_slots = 1u << 21;  // 2 Mi paths in flight: per-round tails and launch gaps amortise (pool sweep)
     if (const char* e = getenv("RT_WF_SLOTS")) n_slots = std::max(1024u, (unsigned int)strtoul(e, nullptr, 10));
     int rc = ensure_state(s, n_slots);
     if (rc != RT_OK) return rc;

@@ -30,6 +30,7 @@ struct DeviceGuard {  // run on the scene's device, restore the caller's afterwa
 };
 
 struct WavefrontState;  // rt_wavefront.cu
+struct WarpfrontState;  // rt_warpfront.cu
 
 DRenderParams device_params(const RtParams* p, int first_sample, int spi, int chunks);
 
@@ -50,7 +51,8 @@ struct RtScene {
     size_t scratch_values = 0;
     unsigned long long* d_rays = nullptr;
     cudaEvent_t ev0 = nullptr, ev1 = nullptr;
-    rtb::WavefrontState* wf = nullptr;  // path pool + queues of the wavefront pipeline, allocated on first use
+    rtb::WavefrontState* wf = nullptr;  // global path pool + queues (RT_PIPELINE_WAVEFRONT_GLOBAL), allocated on first use
+    rtb::WarpfrontState* wa = nullptr;  // launch state of the shared-memory wavefront (RT_PIPELINE_WAVEFRONT)
 };
 
 namespace rtb {
@@ -60,4 +62,8 @@ int launch_megakernel(const RtScene* s, const DCamera& cam, const RtParams* p, i
 int launch_wavefront(RtScene* s, const DCamera& cam, const RtParams* p, int begin, int count, float* d_accum, cudaStream_t stream,
                      RtProgressFn cb, void* user, int* launches);
 void free_wavefront(RtScene* s);
+int launch_warpfront(RtScene* s, const DCamera& cam, const RtParams* p, int begin, int count, float* d_accum, cudaStream_t stream,
+                     RtProgressFn cb, void* user, int* launches);
+bool warpfront_supports(const RtScene* s, const RtParams* p);
+void free_warpfront(RtScene* s);
 }  // namespace rtb

@@ -72,7 +72,8 @@ def test_closest_hit_matches_oracle(name):
     scene.close()
 
 
-PIPELINES = {"megakernel": abi.RT_PIPELINE_MEGAKERNEL, "wavefront": abi.RT_PIPELINE_WAVEFRONT}
+PIPELINES = {"megakernel": abi.RT_PIPELINE_MEGAKERNEL, "wavefront": abi.RT_PIPELINE_WAVEFRONT,
+             "wavefront_smem": abi.RT_PIPELINE_WAVEFRONT_SMEM}
 
 
 @pytest.mark.parametrize("pipeline", list(PIPELINES))
@@ -125,12 +126,14 @@ def test_wavefront_and_megakernel_agree(name, aspect):
         r.pipeline = pid
         rgb, accum = r.render_arrays()
         out[pname] = (rgb, accum.astype(np.float64), r.stats)
-    a, b = out["megakernel"], out["wavefront"]
-    assert a[2]["paths"] == b[2]["paths"] == W * H * spp
-    assert abs(a[2]["rays"] - b[2]["rays"]) <= 1e-3 * a[2]["rays"]
-    close = np.isclose(a[1], b[1], rtol=1e-4, atol=1e-4 * a[1].mean()).all(axis=2)
-    assert close.mean() > 0.98, close.mean()
-    assert abs(a[1].mean() - b[1].mean()) < 2e-3 * a[1].mean()
+    a = out["megakernel"]
+    for other in ("wavefront", "wavefront_smem"):
+        b = out[other]
+        assert a[2]["paths"] == b[2]["paths"] == W * H * spp
+        assert abs(a[2]["rays"] - b[2]["rays"]) <= 1e-3 * a[2]["rays"], other
+        close = np.isclose(a[1], b[1], rtol=1e-4, atol=1e-4 * a[1].mean()).all(axis=2)
+        assert close.mean() > 0.98, (other, close.mean())
+        assert abs(a[1].mean() - b[1].mean()) < 2e-3 * a[1].mean(), other
     scene.close()
 
 
@@ -148,7 +151,8 @@ def test_wavefront_many_rounds_small_pool(monkeypatch):
         r.pipeline = pid
         _, accum = r.render_arrays()
         res[pname] = (accum.astype(np.float64), r.stats)
-    assert abs(res["megakernel"][1]["rays"] - res["wavefront"][1]["rays"]) <= 2e-3 * res["megakernel"][1]["rays"]
-    close = np.isclose(res["megakernel"][0], res["wavefront"][0], rtol=1e-4, atol=1e-3).all(axis=2)
-    assert close.mean() > 0.97, close.mean()
+    for other in ("wavefront", "wavefront_smem"):
+        assert abs(res["megakernel"][1]["rays"] - res[other][1]["rays"]) <= 2e-3 * res["megakernel"][1]["rays"]
+        close = np.isclose(res["megakernel"][0], res[other][0], rtol=1e-4, atol=1e-3).all(axis=2)
+        assert close.mean() > 0.97, (other, close.mean())
     scene.close()
