@@ -217,15 +217,19 @@ def run_b200(args):
     paths_per_step = WIDTH * HEIGHT * spp * world_size
     value = paths_per_step * args.steps / (ms_total / 1e3) / 1e6
 
-    # ---- kernel-only timing of the dominant kernel (CUDA events on the launching stream, no flush/reduce/tonemap)
+    # ---- the render region alone (CUDA events recorded by the library on the launching stream around ALL kernels of the
+    # pipeline; no flush / reduce / tonemap): the numerator of the roofline figure
     p = params(200000)
     st = abi.RtStats()
     accum.zero_()
     torch.cuda.synchronize()
     abi.check(lib.rt_render_accumulate_device(scene.handle, C.byref(cam.c), C.byref(p), accum.data_ptr(), stream.cuda_stream, C.byref(st)))
-    kernel_ms = st.device_ms / max(st.kernel_launches, 1)
-    paths_per_launch = WIDTH * HEIGHT * spp / max(st.kernel_launches, 1)
+    render_ms = st.device_ms
     rays_per_path = st.rays / max(st.paths, 1)
+    pipeline_used = {abi.RT_PIPELINE_MEGAKERNEL: "megakernel", abi.RT_PIPELINE_WAVEFRONT: "wavefront",
+                     abi.RT_PIPELINE_WAVEFRONT_SMEM: "wavefront_smem"}.get(st.pipeline_used, str(st.pipeline_used))
+    kernels = {"megakernel": "render_items_kernel", "wavefront": "wf_extend_kernel + wf_shade_kernel (one pair per round)",
+               "wavefront_smem": "warpfront_kernel"}.get(pipeline_used, "?")
 
     # ---- end to end through the public host API with HOST buffers: scene upload + render + readback, every step
     e2e = None
@@ -266,26 +270,27 @@ def run_b200(args):
         peaks, how = measured_peaks()
         n_sm = torch.cuda.get_device_properties(local_rank).multi_processor_count
         fp32_peak = n_sm * 128 * 2 * float(peaks.get("sm_max_mhz", 1965.0)) * 1e6 / 1e12
-        flops = algo_flops_per_path() * paths_per_launch
-        achieved = flops / (kernel_ms / 1e3) / 1e12
-        hbm_bytes = 3 * 4 * WIDTH * HEIGHT * (spp / max(args.samples_per_item or 16, 1)) / max(st.kernel_launches, 1)
+        flops = algo_flops_per_path() * WIDTH * HEIGHT * spp
+        achieved = flops / (render_ms / 1e3) / 1e12
+        accum_bytes = 3 * 4 * WIDTH * HEIGHT * spp  # one float RED per channel per terminated path (upper bound)
         line = {
             "metric": "Mpaths/s", "value": value, "unit": "Mpaths/s", "n_gpus": world_size, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": ms_total / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
             "data": "synthetic",
             "config": {"workload": f"C4 {WORLD} {WIDTH}x{HEIGHT} seed {SEED} max_depth {MAX_DEPTH}", "spp_per_step_per_gpu": spp,
-                       "paths_per_step": paths_per_step, "job_spp": JOB_SPP, "pipeline": args.pipeline,
+                       "paths_per_step": paths_per_step, "job_spp": JOB_SPP, "pipeline": pipeline_used,
                        "parallelism": f"sample-slices x{world_size} + ncclReduce(sum) of the fp32 accumulation buffer",
                        "l2": "256 MB flush write between steps (inside the timed region)"},
             "clocks": clocks,
             "e2e": e2e,
             "gpu_launches": int(launches[0]) * args.steps,
             "roofline": {"bound": "fp32", "achieved": achieved, "peak": fp32_peak, "unit": "TFLOP/s", "frac": achieved / fp32_peak,
-                         "traffic": None, "kernel": "render_items_kernel", "kernel_ms": kernel_ms,
+                         "traffic": None, "kernel": kernels, "kernel_ms": render_ms, "kernel_launches": st.kernel_launches,
+                         "paths_per_kernel_ms": WIDTH * HEIGHT * spp,
                          "algorithmic_flops_per_path": algo_flops_per_path(), "algorithmic_bytes_per_path": algo_bytes_per_path(),
                          "peak_source": f"{n_sm} SMs x 128 lanes x 2 x sm_max_mhz from MEASURED_PEAKS.json ({how}); no measured FP32 peak exists",
-                         "hbm": {"achieved_gbs": hbm_bytes / (kernel_ms / 1e3) / 1e9, "peak_gbs": peaks.get("hbm_gbs"),
-                                 "note": "accumulation-buffer atomics only; the scene is L1/L2 resident"}},
+                         "hbm": {"achieved_gbs": accum_bytes / (render_ms / 1e3) / 1e9, "peak_gbs": peaks.get("hbm_gbs"),
+                                 "note": "algorithmic HBM bytes = accumulation-buffer REDs only; the scene (~100 KB + 2 MB texture) is L1/L2 resident"}},
             "cpu_baseline": cpu,
             "rays_per_path": rays_per_path, "mrays_per_s": value * rays_per_path,
         }
