@@ -30,11 +30,11 @@ import numpy as np  # noqa: E402
 WORLD, SEED, WIDTH, HEIGHT, ASPECT, MAX_DEPTH, JOB_SPP = "final_scene", 42, 800, 800, 1.0, 50, 10000
 
 # Algorithmic work of the REFERENCE's traversal per camera path on C4, counted by the oracle's instrumentation
-# (800x800, 16 spp, seed 42; see DESIGN.md "Algorithmic work").  flops = 27*aabb + 45*sphere + 15*rect + 12*xform
+# (tools/algo_work.py: 800x800, 16 spp, seed 42).  flops = 27*aabb + 45*sphere + 15*rect + 12*xform
 # + 40*medium + shade terms; bytes = 32 B per node / primitive record touched.
-ALGO = {"rays_per_path": 4.10, "aabb": 65.6, "sphere": 42.4, "rect": 59.8, "xform": 8.2, "medium": 8.2,
-        "lambertian": 0.865, "metal": 0.030, "dielectric": 0.308, "isotropic": 1.92, "perlin": 0.066, "image": 0.068,
-        "background": 0.886}
+ALGO = {"rays_per_path": 4.159, "aabb": 66.59, "sphere": 42.99, "rect": 60.77, "xform": 8.318, "medium": 8.318,
+        "lambertian": 0.878, "metal": 0.0312, "dielectric": 0.315, "isotropic": 1.963, "perlin": 0.0682, "image": 0.0695,
+        "background": 0.886}  # tools/algo_work.py 16 (frozen in BASELINE.md section 4)
 
 
 def algo_flops_per_path():
@@ -311,8 +311,8 @@ def main():
     ap.add_argument("--pipeline", default="auto", choices=["auto", "megakernel", "wavefront", "wavefront_smem"])
     ap.add_argument("--samples-per-item", type=int, default=0)
     ap.add_argument("--e2e-steps", type=int, default=2)
-    ap.add_argument("--cpu-spp", type=int, default=8, help="spp of the bounded CPU-baseline sample (0 = skip)")
-    ap.add_argument("--ref-spp", type=int, default=4, help="spp per step of --impl reference")
+    ap.add_argument("--cpu-spp", type=int, default=64, help="spp of the bounded CPU-baseline sample (0 = skip)")
+    ap.add_argument("--ref-spp", type=int, default=32, help="spp per step of --impl reference")
     args = ap.parse_args()
     if args.impl == "reference":
         return run_reference(args)

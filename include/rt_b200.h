@@ -220,6 +220,18 @@ int rt_tonemap_device(const float* d_accum_rgb, int32_t* d_rgb, int32_t n_pixels
                       int device, void* stream);
 
 /*
+ * rt_render over several GPUs of one process (the reference's row-parallel rayon loop, raytrace.rs:176-185, becomes
+ * sample slices): scenes[g] is the same description created on a distinct device; device g renders every pixel for
+ * the g-th slice of the sample range (rt_sample_slice), the float accumulation buffers are summed onto scenes[0]'s
+ * device with one ncclReduce, and that device tonemaps.  NCCL is bound at run time (dlopen libnccl.so.2);
+ * RT_ERR_UNSUPPORTED if it cannot be loaded.  n_scenes == 1 is rt_render.  Buffers and callback as in rt_render.
+ */
+int rt_render_multi(RtScene* const* scenes, int32_t n_scenes, const RtCamera* cam, const RtParams* params, float* accum_rgb,
+                    int32_t* rgb, RtProgressFn cb, void* user, RtStats* stats);
+/* part `part` of `n_parts` of the sample range: contiguous, disjoint, covering, sizes differ by at most one */
+void rt_sample_slice(int32_t sample_begin, int32_t sample_count, int32_t n_parts, int32_t part, int32_t* begin, int32_t* count);
+
+/*
  * Hittable::hit for a batch of rays (test entry point, SURVEY §8c level 2).
  *   node: index of a node of the description the scene was created from; the
  *         closest hit of that subtree is returned (root = whole world, media excluded

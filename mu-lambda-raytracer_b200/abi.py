@@ -97,6 +97,9 @@ PROTOTYPES = {
                             RtProgressFn, C.c_void_p, C.POINTER(RtStats)]),
     "rt_render_accumulate_device": (C.c_int, [C.c_void_p, C.POINTER(RtCamera), C.POINTER(RtParams), C.c_void_p,
                                               C.c_void_p, C.POINTER(RtStats)]),
+    "rt_render_multi": (C.c_int, [C.POINTER(C.c_void_p), C.c_int32, C.POINTER(RtCamera), C.POINTER(RtParams), C.c_void_p,
+                                  C.c_void_p, RtProgressFn, C.c_void_p, C.POINTER(RtStats)]),
+    "rt_sample_slice": (None, [C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.POINTER(C.c_int32), C.POINTER(C.c_int32)]),
     "rt_tonemap_device": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int32, C.c_int32, C.c_int, C.c_void_p]),
     "rt_intersect_batch": (C.c_int, [C.c_void_p, C.c_int32, C.c_void_p, C.c_int64, C.POINTER(RtHit)]),
     "rt_texture_value_batch": (C.c_int, [C.c_void_p, C.c_int32, C.c_void_p, C.c_int64, C.c_void_p]),

@@ -53,7 +53,7 @@ def build(force=False, verbose=False):
             if verbose and out:
                 print(out)
         objs.append(o)
-    for src in ("rt_api.cu", "rt_wavefront.cu", "rt_warpfront.cu"):
+    for src in ("rt_api.cu", "rt_wavefront.cu", "rt_warpfront.cu", "rt_multi.cu"):
         cu = os.path.join(CSRC, src)
         cuo = os.path.join(bdir, src + ".o")
         if force or _newer(cuo, [cu] + headers):
@@ -64,7 +64,7 @@ def build(force=False, verbose=False):
                 print(out)
         objs.append(cuo)
     if force or _newer(OUT, objs):
-        _run([_nvcc(), "-shared", "-o", OUT] + objs + ["-gencode", "arch=compute_100a,code=sm_100a", "-cudart", "static"])
+        _run([_nvcc(), "-shared", "-o", OUT] + objs + ["-gencode", "arch=compute_100a,code=sm_100a", "-cudart", "static", "-ldl", "-lpthread"])
     main_src = os.path.join(CSRC, "main.cpp")
     if os.path.exists(main_src) and (force or _newer(CLI, [main_src, OUT] + headers)):
         _run(["g++"] + CXX_FLAGS + [main_src, "-o", CLI, "-L" + HERE, "-lrt_b200", "-Wl,-rpath,$ORIGIN"])

@@ -141,8 +141,9 @@ def compare_surface(g, o, rays, grazing=0.02, tol=1e-5):
     dlen = np.linalg.norm(rays[:, 3:6], axis=1)
     dirn = rays[:, 3:6] / dlen[:, None]
     cos = np.abs(np.sum(dirn * o["normal"], axis=1))
+    cos_g = np.abs(np.sum(dirn * g["normal"].astype(np.float64), axis=1))  # where only the device hit, judge grazing by ITS normal
     mism = ohit != ghit
-    hard = mism & ~(ohit & (cos < grazing))
+    hard = mism & ~(ohit & (cos < grazing)) & ~(ghit & ~ohit & (cos_g < grazing))
     both = ohit & ghit & (cos >= grazing)
     scale = np.abs(rays[:, :3]).max(axis=1) + np.abs(o["t"]) * dlen + 1.0
     err = np.abs(g["t"].astype(np.float64) - o["t"]) * dlen / scale
