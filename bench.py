@@ -158,7 +158,7 @@ def run_b200(args):
     spp = args.spp
     total_spp = spp * world_size  # the image every step produces has spp samples from each GPU
     pipeline = {"auto": abi.RT_PIPELINE_AUTO, "megakernel": abi.RT_PIPELINE_MEGAKERNEL, "wavefront": abi.RT_PIPELINE_WAVEFRONT,
-                "wavefront_smem": abi.RT_PIPELINE_WAVEFRONT_SMEM}[args.pipeline]
+                "wavefront_smem": abi.RT_PIPELINE_WAVEFRONT_SMEM, "persistent": abi.RT_PIPELINE_PERSISTENT}[args.pipeline]
 
     def params(step):
         p = abi.RtParams()
@@ -227,9 +227,9 @@ def run_b200(args):
     render_ms = st.device_ms
     rays_per_path = st.rays / max(st.paths, 1)
     pipeline_used = {abi.RT_PIPELINE_MEGAKERNEL: "megakernel", abi.RT_PIPELINE_WAVEFRONT: "wavefront",
-                     abi.RT_PIPELINE_WAVEFRONT_SMEM: "wavefront_smem"}.get(st.pipeline_used, str(st.pipeline_used))
+                     abi.RT_PIPELINE_WAVEFRONT_SMEM: "wavefront_smem", abi.RT_PIPELINE_PERSISTENT: "persistent"}.get(st.pipeline_used, str(st.pipeline_used))
     kernels = {"megakernel": "render_items_kernel", "wavefront": "wf_extend_kernel + wf_shade_kernel (one pair per round)",
-               "wavefront_smem": "warpfront_kernel"}.get(pipeline_used, "?")
+               "wavefront_smem": "warpfront_kernel", "persistent": "persist_kernel"}.get(pipeline_used, "?")
 
     # ---- end to end through the public host API with HOST buffers: scene upload + render + readback, every step
     e2e = None
@@ -308,7 +308,7 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--spp", type=int, default=1000, help="samples per pixel per step per GPU")
-    ap.add_argument("--pipeline", default="auto", choices=["auto", "megakernel", "wavefront", "wavefront_smem"])
+    ap.add_argument("--pipeline", default="auto", choices=["auto", "megakernel", "wavefront", "wavefront_smem", "persistent"])
     ap.add_argument("--samples-per-item", type=int, default=0)
     ap.add_argument("--e2e-steps", type=int, default=2)
     ap.add_argument("--cpu-spp", type=int, default=64, help="spp of the bounded CPU-baseline sample (0 = skip)")

@@ -143,9 +143,11 @@ typedef struct RtCamera {
  * RT_PIPELINE_WAVEFRONT_SMEM the same stages inside one persistent kernel, every warp keeping its own path pool and
  *                            queues in shared memory (evaluated alternative)
  * RT_PIPELINE_MEGAKERNEL     one thread per pixel x run of samples, no queues (the comparator north_star asks for)
+ * RT_PIPELINE_PERSISTENT     the wavefront stages inside one resident kernel: two paths per lane (registers + shared
+ *                            memory), warp ballots choose between the extend and the shade stage, no global queues
  * RT_PIPELINE_AUTO           the pipeline measured fastest on B200 for the scene
  */
-enum { RT_PIPELINE_AUTO = 0, RT_PIPELINE_MEGAKERNEL = 1, RT_PIPELINE_WAVEFRONT = 2, RT_PIPELINE_WAVEFRONT_SMEM = 3 };
+enum { RT_PIPELINE_AUTO = 0, RT_PIPELINE_MEGAKERNEL = 1, RT_PIPELINE_WAVEFRONT = 2, RT_PIPELINE_WAVEFRONT_SMEM = 3, RT_PIPELINE_PERSISTENT = 4 };
 
 /* RenderingParams (raytrace.rs:50-55) + max_depth (main.rs:72) + device-side knobs */
 typedef struct RtParams {

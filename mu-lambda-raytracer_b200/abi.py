@@ -15,7 +15,7 @@ RT_NODE_TRANSLATE, RT_NODE_ROTATE, RT_NODE_MEDIUM, RT_NODE_BVH, RT_NODE_LIST = 6
 RT_MAT_LAMBERTIAN, RT_MAT_METAL, RT_MAT_DIELECTRIC, RT_MAT_DIFFUSE_LIGHT, RT_MAT_ISOTROPIC = 1, 2, 3, 4, 5
 RT_TEX_SOLID, RT_TEX_CHECKER, RT_TEX_NOISE, RT_TEX_IMAGE = 1, 2, 3, 4
 RT_BG_BLACK, RT_BG_GRADIENT = 0, 1
-RT_PIPELINE_AUTO, RT_PIPELINE_MEGAKERNEL, RT_PIPELINE_WAVEFRONT, RT_PIPELINE_WAVEFRONT_SMEM = 0, 1, 2, 3
+RT_PIPELINE_AUTO, RT_PIPELINE_MEGAKERNEL, RT_PIPELINE_WAVEFRONT, RT_PIPELINE_WAVEFRONT_SMEM, RT_PIPELINE_PERSISTENT = 0, 1, 2, 3, 4
 RT_PERLIN_POINTS = 1024
 
 

@@ -223,7 +223,8 @@ int main(int argc, char** argv) {
     uint64_t render_seed = (opt.count("seed") && !randomized_rendering) ? world_seed : (((uint64_t)rd() << 32) ^ (uint64_t)rd());
     long long gpus = parse_int(opt["gpus"], "gpus");
     static const std::map<std::string, int> pipelines = {{"auto", RT_PIPELINE_AUTO}, {"megakernel", RT_PIPELINE_MEGAKERNEL},
-                                                         {"wavefront", RT_PIPELINE_WAVEFRONT}, {"wavefront_smem", RT_PIPELINE_WAVEFRONT_SMEM}};
+                                                         {"wavefront", RT_PIPELINE_WAVEFRONT}, {"wavefront_smem", RT_PIPELINE_WAVEFRONT_SMEM},
+                                                         {"persistent", RT_PIPELINE_PERSISTENT}};
     if (!pipelines.count(opt["pipeline"])) usage_error("'" + opt["pipeline"] + "' isn't a valid value for '--pipeline <pipeline>'");
 
     // ---- World::build (main.rs:185-188)

@@ -183,6 +183,7 @@ void free_scene(RtScene* s) {
         if (s->ev1) cudaEventDestroy(s->ev1);
         free_wavefront(s);
         free_warpfront(s);
+        free_persist(s);
     }
     if (s->desc) rtb::free_desc(s->desc);
     delete s;
@@ -217,7 +218,7 @@ int validate_render(const RtScene* scene, const RtCamera* cam, const RtParams* p
     if ((long long)p->width * p->height > (1ll << 31) / 3) return set_error(RT_ERR_INVALID, "render: image too large");
     if (p->samples_per_pixel <= 0 || p->max_depth < 0) return set_error(RT_ERR_INVALID, "render: samples_per_pixel must be > 0 and max_depth >= 0");
     if (p->sample_begin < 0 || p->sample_count < 0) return set_error(RT_ERR_INVALID, "render: negative sample range");
-    if (p->pipeline < RT_PIPELINE_AUTO || p->pipeline > RT_PIPELINE_WAVEFRONT_SMEM) return set_error(RT_ERR_INVALID, "render: unknown pipeline");
+    if (p->pipeline < RT_PIPELINE_AUTO || p->pipeline > RT_PIPELINE_PERSISTENT) return set_error(RT_ERR_INVALID, "render: unknown pipeline");
     return RT_OK;
 }
 
@@ -276,6 +277,7 @@ int run_pipeline(RtScene* s, const DCamera& cam, const RtParams* p, int begin, i
     *used = pick_pipeline(s, p);
     if (*used == RT_PIPELINE_WAVEFRONT) return launch_wavefront(s, cam, p, begin, count, d_accum, stream, cb, user, launches);
     if (*used == RT_PIPELINE_WAVEFRONT_SMEM) return launch_warpfront(s, cam, p, begin, count, d_accum, stream, cb, user, launches);
+    if (*used == RT_PIPELINE_PERSISTENT) return launch_persist(s, cam, p, begin, count, d_accum, stream, cb, user, launches);
     return launch_megakernel(s, cam, p, begin, count, d_accum, stream, cb, user, launches);
 }
 

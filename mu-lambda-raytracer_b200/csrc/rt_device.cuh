@@ -118,7 +118,12 @@ struct Ray {
 };
 
 // ------------------------------------------------------------------ Philox4x32-10 (Salmon et al., SC'11)
-RTB_DEV void philox4x32_10(uint32_t c0, uint32_t c1, uint32_t c2, uint32_t c3, uint32_t k0, uint32_t k1, uint32_t out[4]) {
+// Out of line on the device: three call sites per path segment (camera, media, scatter) share one copy of the
+// ten rounds, which keeps the instruction footprint of the shade stage inside the instruction cache.
+struct U4 {
+    uint32_t x, y, z, w;
+};
+RTB_DEV_NOINLINE U4 philox4x32_10v(uint32_t c0, uint32_t c1, uint32_t c2, uint32_t c3, uint32_t k0, uint32_t k1) {
     const uint32_t M0 = 0xD2511F53u, M1 = 0xCD9E8D57u, W0 = 0x9E3779B9u, W1 = 0xBB67AE85u;
 #pragma unroll
     for (int round = 0; round < 10; ++round) {
@@ -128,7 +133,11 @@ RTB_DEV void philox4x32_10(uint32_t c0, uint32_t c1, uint32_t c2, uint32_t c3, u
         c0 = n0, c1 = lo1, c2 = n2, c3 = lo0;
         k0 += W0, k1 += W1;
     }
-    out[0] = c0, out[1] = c1, out[2] = c2, out[3] = c3;
+    return U4{c0, c1, c2, c3};
+}
+RTB_DEV void philox4x32_10(uint32_t c0, uint32_t c1, uint32_t c2, uint32_t c3, uint32_t k0, uint32_t k1, uint32_t out[4]) {
+    U4 r = philox4x32_10v(c0, c1, c2, c3, k0, k1);
+    out[0] = r.x, out[1] = r.y, out[2] = r.z, out[3] = r.w;
 }
 
 // one stream per camera path: counter = (pixel, sample, draw, tag), key = seed
@@ -194,17 +203,23 @@ RTB_DEV int prim_instance(const PrimRec& p) { return (int)((p.meta >> PRIM_INST_
 // large sphere (|c| << r^2); those cases (the r = 1000 ground of `random` seen from just above it) take the f64 path.
 RTB_DEV bool sphere_needs_f64(const PrimRec& p, float c) { return (p.meta & PRIM_BIG) && fabsf(c) < 0.05f * p.v3 * p.v3; }
 
-RTB_DEV void sphere_roots_f64(const DSceneView& S, const PrimRec& p, const Ray& r, bool& real, float& t0, float& t1) {
-    const DBigSphere& b = S.big[as_uint(p.v4)];
-    double ocx = (double)r.o.x - b.c[0], ocy = (double)r.o.y - b.c[1], ocz = (double)r.o.z - b.c[2];
-    double dx = r.d.x, dy = r.d.y, dz = r.d.z;
+struct Roots {
+    float t0, t1;
+    int real;
+};
+// out of line: rare (only next to the surface of an |r| >= 100 sphere) and large (f64 divide and square root)
+RTB_DEV_NOINLINE Roots sphere_roots_f64(double cx, double cy, double cz, double radius, float ox, float oy, float oz, float ddx, float ddy, float ddz) {
+    double ocx = (double)ox - cx, ocy = (double)oy - cy, ocz = (double)oz - cz;
+    double dx = ddx, dy = ddy, dz = ddz;
     double a = dx * dx + dy * dy + dz * dz;
     double hb = ocx * dx + ocy * dy + ocz * dz;
-    double c = ocx * ocx + ocy * ocy + ocz * ocz - b.r * b.r;
+    double c = ocx * ocx + ocy * ocy + ocz * ocz - radius * radius;
     double disc = hb * hb - a * c;
-    real = !(disc < 0.0);
-    double sq = sqrt(real ? disc : 0.0);
-    t0 = (float)((-hb - sq) / a), t1 = (float)((-hb + sq) / a);
+    Roots out;
+    out.real = !(disc < 0.0);
+    double sq = sqrt(out.real ? disc : 0.0);
+    out.t0 = (float)((-hb - sq) / a), out.t1 = (float)((-hb + sq) / a);
+    return out;
 }
 
 // both roots of the sphere quadratic, t0 <= t1 (shapes.rs:57-68); false when the discriminant is negative
@@ -213,9 +228,10 @@ RTB_DEV bool sphere_roots(const DSceneView& S, const PrimRec& p, const Ray& r, f
     float a = dot(r.d, r.d), hb = dot(oc, r.d), inv_a = 1.0f / a;
     float c = dot(oc, oc) - p.v3 * p.v3;
     if (sphere_needs_f64(p, c)) {
-        bool real;
-        sphere_roots_f64(S, p, r, real, t0, t1);
-        return real;
+        const DBigSphere& b = S.big[as_uint(p.v4)];
+        Roots q = sphere_roots_f64(b.c[0], b.c[1], b.c[2], b.r, r.o.x, r.o.y, r.o.z, r.d.x, r.d.y, r.d.z);
+        t0 = q.t0, t1 = q.t1;
+        return q.real != 0;
     }
     // discriminant from the perpendicular offset |oc - (hb/a) d|^2: no cancellation for distant origins
     V3 l = oc - (hb * inv_a) * r.d;
@@ -424,11 +440,19 @@ RTB_DEV void sample_media(const DSceneView& S, const Ray& r, float tmin, const f
 }
 
 // ------------------------------------------------------------------ textures
-RTB_DEV void sphere_uv(V3 n, float& u, float& v) {  // shapes.rs:44-55
+struct UV {
+    float u, v;
+};
+// out of line: only image-textured spheres need it, and acosf / atan2f are long
+RTB_DEV_NOINLINE UV sphere_uv_v(float nx, float ny, float nz) {  // shapes.rs:44-55
     const float pi = 3.14159265358979f;
-    float theta = acosf(fminf(fmaxf(-n.y, -1.0f), 1.0f));
-    float phi = atan2f(-n.z, n.x) + pi;
-    u = phi / (2.0f * pi), v = theta / pi;
+    float theta = acosf(fminf(fmaxf(-ny, -1.0f), 1.0f));
+    float phi = atan2f(-nz, nx) + pi;
+    return UV{phi / (2.0f * pi), theta / pi};
+}
+RTB_DEV void sphere_uv(V3 n, float& u, float& v) {
+    UV r = sphere_uv_v(n.x, n.y, n.z);
+    u = r.u, v = r.v;
 }
 
 RTB_DEV float perlin_noise(const float* vec, const unsigned short* perm, V3 p) {  // textures.rs:90-134
@@ -462,11 +486,28 @@ RTB_DEV float perlin_turbulence(const float* vec, const unsigned short* perm, V3
     return fabsf(accum);
 }
 
-RTB_DEV V3 texture_leaf(const DSceneView& S, const DTexture& T, float u, float v, V3 p) {
-    if (T.kind == TEX_NOISE) {  // NoiseTexture::value, textures.rs:163-166 — marble phase on z
+// A NoiseTexture::value the caller evaluates itself (the persistent kernel does it warp-cooperatively: the 56
+// gradient terms of the 7-octave turbulence are spread over the lanes).  tex < 0: nothing pending.
+struct NoiseReq {
+    int tex;  // DTexture index of the NOISE leaf
+    V3 p;     // the hit point (unscaled)
+};
+
+RTB_DEV float noise_value(const DTexture& T, V3 p, float turbulence) {  // NoiseTexture::value, textures.rs:163-166 — marble phase on z
+    return 0.5f * (1.0f + sinf(T.scale * p.z + 10.0f * turbulence));
+}
+
+// req == nullptr: evaluate everything here.  Otherwise a NOISE leaf is left pending in *req and white is returned.
+RTB_DEV V3 texture_leaf(const DSceneView& S, int tex, float u, float v, V3 p, NoiseReq* req) {
+    const DTexture& T = S.texs[tex];
+    if (T.kind == TEX_NOISE) {
+        if (req) {
+            req->tex = tex, req->p = p;
+            return v3(1.f, 1.f, 1.f);
+        }
         const float* vec = S.perlin_vec + (size_t)T.a * RTB_PERLIN_POINTS * 4;
         const unsigned short* perm = S.perlin_perm + (size_t)T.a * RTB_PERLIN_POINTS * 3;
-        float g = 0.5f * (1.0f + sinf(T.scale * p.z + 10.0f * perlin_turbulence(vec, perm, T.scale * p)));
+        float g = noise_value(T, p, perlin_turbulence(vec, perm, T.scale * p));
         return v3(g, g, g);
     }
     if (T.kind == TEX_IMAGE) {  // image_texture.rs:16-28 — nearest texel, v flipped
@@ -483,13 +524,13 @@ RTB_DEV V3 texture_leaf(const DSceneView& S, const DTexture& T, float u, float v
     return v3(T.color[0], T.color[1], T.color[2]);
 }
 
-RTB_DEV V3 texture_value(const DSceneView& S, int tex, float u, float v, V3 p) {
+RTB_DEV V3 texture_value(const DSceneView& S, int tex, float u, float v, V3 p, NoiseReq* req = nullptr) {
     const DTexture& T = S.texs[tex];
     if (T.kind == TEX_CHECKER) {  // textures.rs:40-49
         float sines = sinf(5.0f * p.x) * sinf(5.0f * p.y) * sinf(5.0f * p.z);
-        return texture_leaf(S, S.texs[sines < 0.0f ? T.a : T.b], u, v, p);
+        return texture_leaf(S, sines < 0.0f ? T.a : T.b, u, v, p, req);
     }
-    return texture_leaf(S, T, u, v, p);
+    return texture_leaf(S, tex, u, v, p, req);
 }
 
 RTB_DEV bool texture_needs_uv(const DSceneView& S, int tex) {
@@ -568,64 +609,53 @@ RTB_DEV V3 background_color(const DSceneView& S, const Ray& r) {  // raytrace.rs
               (1.0f - t) * S.bg_bottom[2] + t * S.bg_top[2]);
 }
 
-RTB_DEV V3 material_color(const DSceneView& S, const DMaterial& M, const Surface& s) {
+RTB_DEV V3 material_color(const DSceneView& S, const DMaterial& M, const Surface& s, NoiseReq* req = nullptr) {
     if (M.tex < 0) return v3(M.albedo[0], M.albedo[1], M.albedo[2]);
-    return texture_value(S, M.tex, s.u, s.v, s.p);
+    return texture_value(S, M.tex, s.u, s.v, s.p, req);
 }
 
 // Material::scatter / emit at a surface or medium event.  Returns true when the path goes on (ps updated);
 // otherwise `radiance` is the terminal term (emission, or 0 for an absorbed metal reflection).
-RTB_DEV bool scatter(const DSceneView& S, const DMaterial& M, const Surface& s, const float u[4], PathState& ps, int prim, int face, V3& radiance) {
-    V3 dir, att;
-    switch (M.kind) {
-        case MAT_LAMBERTIAN: {  // materials.rs:25-34: normal + in-ball point flipped into the hemisphere
-            V3 b = sample_unit_ball(u[0], u[1], u[2]);
-            if (!(dot(s.n, b) > 0.0f)) b = -b;
-            dir = s.n + b;
-            if (fabsf(dir.x) < 1e-8f && fabsf(dir.y) < 1e-8f && fabsf(dir.z) < 1e-8f) dir = s.n;
-            att = material_color(S, M, s);
-            break;
-        }
-        case MAT_METAL: {  // materials.rs:51-61
-            V3 ud = normalize(ps.ray.d);
-            dir = ud - (2.0f * dot(ud, s.n)) * s.n;
-            if (M.fuzz > 0.0f) dir = dir + M.fuzz * sample_unit_ball(u[0], u[1], u[2]);
-            if (!(dot(dir, s.n) > 0.0f)) {
-                radiance = v3(0.f, 0.f, 0.f);  // scatter -> None, emit -> 0
-                return false;
-            }
-            att = v3(M.albedo[0], M.albedo[1], M.albedo[2]);
-            break;
-        }
-        case MAT_DIELECTRIC: {  // materials.rs:88-106
-            float ratio = s.front ? 1.0f / M.ior : M.ior;
-            V3 ud = normalize(ps.ray.d);
-            float cos_t = fminf(dot(-ud, s.n), 1.0f);
-            float sin_t = sqrtf(fmaxf(0.0f, 1.0f - cos_t * cos_t));
-            float r0 = (1.0f - ratio) / (1.0f + ratio);
-            r0 = r0 * r0;
-            float x = 1.0f - cos_t;
-            float x2 = x * x;
-            float refl = r0 + (1.0f - r0) * (x * x2 * x2);
-            if (ratio * sin_t > 1.0f || refl > u[3]) {
-                dir = ud - (2.0f * dot(ud, s.n)) * s.n;
-            } else {
-                V3 perp = ratio * (ud + cos_t * s.n);
-                V3 par = -sqrtf(fabsf(1.0f - dot(perp, perp))) * s.n;
-                dir = perp + par;
-            }
-            att = v3(1.f, 1.f, 1.f);
-            break;
-        }
-        case MAT_ISOTROPIC: {  // volumes.rs:77-83: raw in-ball direction
-            dir = sample_unit_ball(u[0], u[1], u[2]);
-            att = material_color(S, M, s);
-            break;
-        }
-        default: {  // MAT_DIFFUSE_LIGHT, materials.rs:119-127: emits from both faces, never scatters
-            radiance = material_color(S, M, s);
-            return false;
-        }
+// With `req`, a noise texture is left pending: the caller multiplies ps.beta (alive) or radiance (emitter) by it.
+RTB_DEV bool scatter(const DSceneView& S, const DMaterial& M, const Surface& s, const float u[4], PathState& ps, int prim, int face, V3& radiance,
+                     NoiseReq* req = nullptr) {
+    // Branch-light: what several material kinds need is computed once by every lane (the lanes of a warp shade
+    // different materials side by side), the kinds then differ by a few selects.
+    const int kind = M.kind;
+    const V3 ball = sample_unit_ball(u[0], u[1], u[2]);  // Lambertian, fuzzy metal, isotropic
+    const V3 ud = normalize(ps.ray.d);                   // metal, dielectric
+    const float udn = dot(ud, s.n);
+    const V3 refl = ud - (2.0f * udn) * s.n;             // reflect(), materials.rs:47-49
+    const V3 color = material_color(S, M, s, req);       // albedo / texture value / emission
+    V3 dir = ball, att = color;                          // MAT_ISOTROPIC, volumes.rs:77-83: raw in-ball direction
+    bool scattered = true;
+    if (kind == MAT_LAMBERTIAN) {  // materials.rs:25-34: normal + in-ball point flipped into the hemisphere
+        V3 b = dot(s.n, ball) > 0.0f ? ball : -ball;
+        dir = s.n + b;
+        if (fabsf(dir.x) < 1e-8f && fabsf(dir.y) < 1e-8f && fabsf(dir.z) < 1e-8f) dir = s.n;
+    } else if (kind == MAT_METAL) {  // materials.rs:51-61 (fuzz == 0 adds nothing)
+        dir = refl + M.fuzz * ball;
+        scattered = dot(dir, s.n) > 0.0f;  // otherwise scatter -> None, emit -> 0
+    } else if (kind == MAT_DIELECTRIC) {  // materials.rs:88-106
+        float ratio = s.front ? 1.0f / M.ior : M.ior;
+        float cos_t = fminf(-udn, 1.0f);
+        float sin_t = sqrtf(fmaxf(0.0f, 1.0f - cos_t * cos_t));
+        float r0 = (1.0f - ratio) / (1.0f + ratio);
+        r0 = r0 * r0;
+        float x = 1.0f - cos_t;
+        float x2 = x * x;
+        float reflectance = r0 + (1.0f - r0) * (x * x2 * x2);
+        V3 perp = ratio * (ud + cos_t * s.n);
+        V3 par = -sqrtf(fabsf(1.0f - dot(perp, perp))) * s.n;
+        dir = (ratio * sin_t > 1.0f || reflectance > u[3]) ? refl : perp + par;
+        att = v3(1.f, 1.f, 1.f);
+    } else if (kind == MAT_DIFFUSE_LIGHT) {  // materials.rs:119-127: emits from both faces, never scatters
+        radiance = color;
+        return false;
+    }
+    if (!scattered) {
+        radiance = v3(0.f, 0.f, 0.f);
+        return false;
     }
     ps.beta = ps.beta * att;
     ps.ray.o = s.p;
@@ -633,6 +663,26 @@ RTB_DEV bool scatter(const DSceneView& S, const DMaterial& M, const Surface& s, 
     ps.origin_prim = prim;
     ps.origin_face = face;
     return true;
+}
+
+// Material::scatter / emit for the event the extend stage found: a medium event (volumes.rs:55-63: normal (1,0,0),
+// front_face, u = v = 0) or a surface hit.  ONE scatter call site for both.
+RTB_DEV bool scatter_event(const DSceneView& S, int medium, int prim, int face, float t, const float u[4], PathState& ps, V3& radiance, NoiseReq* req) {
+    Surface sf;
+    int mat_index;
+    if (medium >= 0) {
+        mat_index = (int)as_uint(ld4(reinterpret_cast<const char*>(S.media + medium) + 32).y);
+        sf.p = ps.ray.o + t * ps.ray.d;
+        sf.n = v3(1.f, 0.f, 0.f), sf.u = 0.f, sf.v = 0.f, sf.front = true;
+        prim = -1, face = 0;
+    } else {
+        PrimRec Pr = load_prim(S.prims + prim);
+        mat_index = Pr.mat;
+        int tex = (int)as_uint(ld4(S.mats + mat_index).y);
+        bool want_uv = tex >= 0 && texture_needs_uv(S, tex);
+        surface_at(S, Pr, ps.ray, t, face, want_uv, sf);
+    }
+    return scatter(S, S.mats[mat_index], sf, u, ps, prim, face, radiance, req);
 }
 
 // One path segment: nearest surface, media, then scatter.  Returns true while the path is alive; when it
@@ -665,23 +715,8 @@ RTB_DEV bool extend_and_shade(const DSceneView& S, PathState& ps, PathRng& rng, 
     }
     float us[4];
     rng_next4(rng, us);
-    Surface s;
     V3 term;
-    bool alive;
-    if (medium >= 0) {  // volumes.rs:55-63: normal (1,0,0), front_face, u = v = 0
-        const DMedium* M = S.media + medium;
-        float4 tail = ld4(reinterpret_cast<const char*>(M) + 32);
-        const DMaterial& mat = S.mats[(int)as_uint(tail.y)];
-        s.p = ps.ray.o + t * ps.ray.d;
-        s.n = v3(1.f, 0.f, 0.f), s.u = 0.f, s.v = 0.f, s.front = true;
-        alive = scatter(S, mat, s, us, ps, -1, 0, term);
-    } else {
-        PrimRec P = load_prim(S.prims + prim);
-        const DMaterial& mat = S.mats[P.mat];
-        bool want_uv = mat.tex >= 0 && texture_needs_uv(S, mat.tex);
-        surface_at(S, P, ps.ray, t, face, want_uv, s);
-        alive = scatter(S, mat, s, us, ps, prim, face, term);
-    }
+    bool alive = scatter_event(S, medium, prim, face, t, us, ps, term, nullptr);
     if (!alive) {
         radiance = ps.beta * term;
     } else if (ps.depth <= 0) {  // the next trace_internal call would return Color::ZERO at once
@@ -789,7 +824,8 @@ RTB_DEV void wf_init_path(const DSceneView& S, const DCamera& cam, const DRender
     wf_init_pixel_sample(S, cam, P, (uint32_t)(path % npix), (uint32_t)P.sample_begin + (uint32_t)(path / npix), s);
 }
 
-RTB_DEV void wf_init_pixel_sample(const DSceneView& S, const DCamera& cam, const DRenderParams& P, uint32_t pixel, uint32_t sample, WfSlot& s) {
+// the camera ray alone (the caller pre-samples the media of segment 0)
+RTB_DEV void wf_init_camera(const DCamera& cam, const DRenderParams& P, uint32_t pixel, uint32_t sample, WfSlot& s) {
     PathRng rng;
     rng.pixel = pixel, rng.sample = sample, rng.draw = 0, rng.k0 = P.seed_lo, rng.k1 = P.seed_hi;
     float u[4];
@@ -799,6 +835,10 @@ RTB_DEV void wf_init_pixel_sample(const DSceneView& S, const DCamera& cam, const
     s.B = f4(r.d.x, r.d.y, r.d.z, as_float((uint32_t)P.max_depth));
     s.C = f4(1.f, 1.f, 1.f, as_float(sample));
     s.D = f4(0.f, 0.f, as_float(0xFFFFFFFFu), 0.f);
+}
+
+RTB_DEV void wf_init_pixel_sample(const DSceneView& S, const DCamera& cam, const DRenderParams& P, uint32_t pixel, uint32_t sample, WfSlot& s) {
+    wf_init_camera(cam, P, pixel, sample, s);
     wf_presample_media(S, P, s, 0);
 }
 
@@ -820,7 +860,8 @@ RTB_DEV int wf_classify(const DSceneView& S, int prim, int face, int mat, int co
 
 // the shade stage for one path: scatter or terminate.  Returns true while alive (slot updated in place, media
 // event of the new ray pre-sampled); otherwise `radiance` is the path's contribution to its pixel.
-RTB_DEV bool wf_shade(const DSceneView& S, const DRenderParams& P, WfSlot& s, V3& radiance) {
+// wf_shade_core: everything but the media pre-sampling of the new ray; `segment_next` = its segment number.
+RTB_DEV bool wf_shade_core(const DSceneView& S, const DRenderParams& P, WfSlot& s, V3& radiance, NoiseReq* req, int& segment_next) {
     PathState ps;
     ps.ray.o = v3(s.A.x, s.A.y, s.A.z), ps.ray.d = v3(s.B.x, s.B.y, s.B.z);
     ps.beta = v3(s.C.x, s.C.y, s.C.z);
@@ -828,6 +869,7 @@ RTB_DEV bool wf_shade(const DSceneView& S, const DRenderParams& P, WfSlot& s, V3
     ps.depth = (int)(flags & WF_DEPTH_MASK);
     int segment = P.max_depth - ps.depth;
     ps.depth -= 1;  // this segment's ray has been traced
+    segment_next = segment + 1;
     ps.origin_prim = -1, ps.origin_face = 0;
     int code = (int)as_uint(s.D.y);
     float t = s.D.x;
@@ -839,36 +881,29 @@ RTB_DEV bool wf_shade(const DSceneView& S, const DRenderParams& P, WfSlot& s, V3
     rng.pixel = as_uint(s.A.w), rng.sample = as_uint(s.C.w), rng.draw = 2u + 2u * (uint32_t)segment, rng.k0 = P.seed_lo, rng.k1 = P.seed_hi;
     float us[4];
     rng_next4(rng, us);
-    Surface sf;
     V3 term;
-    bool alive;
-    if (code & WF_MEDIUM) {
-        int medium = code & 0xFFFF;
-        const DMaterial& mat = S.mats[(int)as_uint(ld4(reinterpret_cast<const char*>(S.media + medium) + 32).y)];
-        sf.p = ps.ray.o + t * ps.ray.d;
-        sf.n = v3(1.f, 0.f, 0.f), sf.u = 0.f, sf.v = 0.f, sf.front = true;
-        alive = scatter(S, mat, sf, us, ps, -1, 0, term);
-    } else {
-        int prim = code & 0xFFFFFF, face = (code >> 24) & 7;
-        PrimRec Pr = load_prim(S.prims + prim);
-        const DMaterial& mat = S.mats[Pr.mat];
-        bool want_uv = mat.tex >= 0 && texture_needs_uv(S, mat.tex);
-        surface_at(S, Pr, ps.ray, t, face, want_uv, sf);
-        alive = scatter(S, mat, sf, us, ps, prim, face, term);
-    }
+    const bool is_medium = (code & WF_MEDIUM) != 0;
+    bool alive = scatter_event(S, is_medium ? (code & 0xFFFF) : -1, code & 0xFFFFFF, (code >> 24) & 7, t, us, ps, term, req);
     if (!alive) {
         radiance = ps.beta * term;
         return false;
     }
     if (ps.depth <= 0) {
         radiance = v3(0.f, 0.f, 0.f);
+        if (req) req->tex = -1;
         return false;
     }
     s.A = f4(ps.ray.o.x, ps.ray.o.y, ps.ray.o.z, s.A.w);
     s.B = f4(ps.ray.d.x, ps.ray.d.y, ps.ray.d.z, as_float((uint32_t)ps.depth | ((uint32_t)ps.origin_face << WF_FACE_SHIFT)));
     s.C = f4(ps.beta.x, ps.beta.y, ps.beta.z, s.C.w);
     s.D.z = as_float((uint32_t)ps.origin_prim);
-    wf_presample_media(S, P, s, segment + 1);
+    return true;
+}
+
+RTB_DEV bool wf_shade(const DSceneView& S, const DRenderParams& P, WfSlot& s, V3& radiance) {
+    int segment_next;
+    if (!wf_shade_core(S, P, s, radiance, nullptr, segment_next)) return false;
+    wf_presample_media(S, P, s, segment_next);
     return true;
 }
 

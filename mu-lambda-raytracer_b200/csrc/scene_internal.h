@@ -31,6 +31,7 @@ struct DeviceGuard {  // run on the scene's device, restore the caller's afterwa
 
 struct WavefrontState;  // rt_wavefront.cu
 struct WarpfrontState;  // rt_warpfront.cu
+struct PersistState;    // rt_persist.cu
 
 DRenderParams device_params(const RtParams* p, int first_sample, int spi, int chunks);
 
@@ -52,6 +53,7 @@ struct RtScene {
     unsigned long long* d_rays = nullptr;
     cudaEvent_t ev0 = nullptr, ev1 = nullptr;
     rtb::WavefrontState* wf = nullptr;  // global path pool + queues (RT_PIPELINE_WAVEFRONT_GLOBAL), allocated on first use
+    rtb::PersistState* ps = nullptr;    // counters of the persistent pipeline (RT_PIPELINE_PERSISTENT)
     rtb::WarpfrontState* wa = nullptr;  // launch state of the shared-memory wavefront (RT_PIPELINE_WAVEFRONT)
 };
 
@@ -66,4 +68,8 @@ int launch_warpfront(RtScene* s, const DCamera& cam, const RtParams* p, int begi
                      RtProgressFn cb, void* user, int* launches);
 bool warpfront_supports(const RtScene* s, const RtParams* p);
 void free_warpfront(RtScene* s);
+int launch_persist(RtScene* s, const DCamera& cam, const RtParams* p, int begin, int count, float* d_accum, cudaStream_t stream,
+                   RtProgressFn cb, void* user, int* launches);
+bool persist_supports(const RtScene* s, const RtParams* p);
+void free_persist(RtScene* s);
 }  // namespace rtb
