@@ -269,7 +269,7 @@ namespace {
 // AUTO resolves to the pipeline measured fastest on B200 for this scene class (see DESIGN.md "Pipelines")
 int pick_pipeline(const RtScene* s, const RtParams* p) {
     if (p->pipeline != RT_PIPELINE_AUTO) return p->pipeline;
-    return warpfront_supports(s, p) ? RT_PIPELINE_WAVEFRONT : RT_PIPELINE_MEGAKERNEL;  // same limits for both wavefronts
+    return persist_supports(s, p) ? RT_PIPELINE_PERSISTENT : RT_PIPELINE_MEGAKERNEL;  // measured fastest on C1-C4
 }
 
 int run_pipeline(RtScene* s, const DCamera& cam, const RtParams* p, int begin, int count, float* d_accum, cudaStream_t stream, RtProgressFn cb,

@@ -337,14 +337,32 @@ RTB_DEV bool hit_prim(const DSceneView& S, const PrimRec& p, const Ray& r, float
 }
 
 // ------------------------------------------------------------------ BVH traversal
-RTB_DEV bool slab_node(const float4& n0, const float4& n1, V3 o, V3 inv, float tmin, float tmax, float& tn_out) {
-    float ax = (n0.x - o.x) * inv.x, bx = (n1.x - o.x) * inv.x;
-    float ay = (n0.y - o.y) * inv.y, by = (n1.y - o.y) * inv.y;
-    float az = (n0.z - o.z) * inv.z, bz = (n1.z - o.z) * inv.z;
+// Per-ray constants of the node test.  The slab distances are evaluated as fma(n, inv, -o*inv): 6 FFMA per box instead
+// of 6 FADD + 6 FMUL.  That form rounds o*inv before the subtraction, so a crossing carries an absolute error of about
+// ulp(o*inv); `pad` (4 ulp of the largest |o*inv|) widens the far side by that much, which keeps the test conservative:
+// a box the exact slabs would keep is never culled (leaf primitives are tested exactly, with the ray itself).
+// Zero direction components are replaced by +-2^-80 (as in Aila & Laine's kernels) so that inv stays finite.
+struct NodeRay {
+    V3 inv, noi;  // 1/d and -o/d
+    float pad;
+};
+RTB_DEV NodeRay node_ray(const Ray& r) {
+    const float tiny = 8.271806e-25f;  // 2^-80
+    NodeRay n;
+    n.inv = v3(1.0f / (fabsf(r.d.x) > tiny ? r.d.x : copysignf(tiny, r.d.x)), 1.0f / (fabsf(r.d.y) > tiny ? r.d.y : copysignf(tiny, r.d.y)),
+               1.0f / (fabsf(r.d.z) > tiny ? r.d.z : copysignf(tiny, r.d.z)));
+    n.noi = v3(-r.o.x * n.inv.x, -r.o.y * n.inv.y, -r.o.z * n.inv.z);
+    n.pad = 4.7683716e-7f * fmaxf(fmaxf(fabsf(n.noi.x), fabsf(n.noi.y)), fabsf(n.noi.z));  // 2^-21
+    return n;
+}
+RTB_DEV bool slab_node(const float4& n0, const float4& n1, const NodeRay& q, float tmin, float tmax, float& tn_out) {
+    float ax = fmaf(n0.x, q.inv.x, q.noi.x), bx = fmaf(n1.x, q.inv.x, q.noi.x);
+    float ay = fmaf(n0.y, q.inv.y, q.noi.y), by = fmaf(n1.y, q.inv.y, q.noi.y);
+    float az = fmaf(n0.z, q.inv.z, q.noi.z), bz = fmaf(n1.z, q.inv.z, q.noi.z);
     float tn = fmaxf(fmaxf(fminf(ax, bx), fminf(ay, by)), fmaxf(fminf(az, bz), tmin));
     float tf = fminf(fminf(fmaxf(ax, bx), fmaxf(ay, by)), fminf(fmaxf(az, bz), tmax));
     tn_out = tn;
-    return tn <= tf * 1.0000004f;  // slightly conservative: never cull a box the exact slabs would keep
+    return tn <= fmaf(tf, 1.0000004f, q.pad);  // conservative: relative slack for the roundings of t, `pad` for those of o*inv
 }
 
 // Closest surface hit with t in [tmin, +inf): replaces HittableList::hit + BHV::hit + the shapes.
@@ -353,7 +371,7 @@ RTB_DEV void closest_hit(const DSceneView& S, const Ray& r, float tmin, float tm
                          int& face_best) {
     t_best = tmax, prim_best = -1, face_best = 0;
     if (S.n_prims == 0) return;
-    V3 inv = v3(1.0f / r.d.x, 1.0f / r.d.y, 1.0f / r.d.z);
+    const NodeRay nr = node_ray(r);
     int stack[RTB_BVH_STACK];
     int sp = 0;
     int cur = (int)as_uint(ld4(S.nodes).w);  // link of the root (its own box is never tested)
@@ -373,8 +391,8 @@ RTB_DEV void closest_hit(const DSceneView& S, const Ray& r, float tmin, float tm
             const char* base = reinterpret_cast<const char*>(S.nodes + cur);
             float4 l0 = ld4(base), l1 = ld4(base + 16), r0 = ld4(base + 32), r1 = ld4(base + 48);
             float tl, tr;
-            bool hl = slab_node(l0, l1, r.o, inv, tmin, t_best, tl);
-            bool hr = slab_node(r0, r1, r.o, inv, tmin, t_best, tr);
+            bool hl = slab_node(l0, l1, nr, tmin, t_best, tl);
+            bool hr = slab_node(r0, r1, nr, tmin, t_best, tr);
             int ll = (int)as_uint(l0.w), lr = (int)as_uint(r0.w);
             if (hl && hr) {
                 bool left_first = tl <= tr;

@@ -27,13 +27,19 @@ namespace rtb {
 
 #define PS_THREADS 128
 #define PS_DONE ((int)0x80000000)
-#define PS_MIN_DESCEND 8   // lanes that must still be descending inner nodes for the inner loop to keep going
-#define PS_LEAVE 4         // lanes that must have finished before the warp leaves the traversal loop to swap paths
+#define PS_MIN_DESCEND 6   // lanes that must still be descending inner nodes for the inner loop to keep going
+#define PS_LEAVE 8         // lanes that must have finished before the warp leaves the traversal loop to swap paths
 #define PS_WORK 24         // lanes with shading / regeneration work pending that trigger a shade phase ...
-#define PS_STALL 6         // ... or lanes that cannot traverse at all (both of their paths wait for the shade phase)
+#define PS_STALL 14        // ... or lanes that cannot traverse at all (both of their paths wait for the shade phase)
+#define PS_MIN_BLOCKS 5    // resident blocks per SM the kernel is compiled for: 96 registers, no spills (6/7/8 blocks spill and measured 4/6/11 % slower)
 #define PS_CHUNK 256u      // camera paths a warp reserves per atomic
 
 enum { ST_EMPTY = 0, ST_TRAV = 1, ST_DONE = 2, ST_READY = 3 };
+
+// scheduling thresholds (defaults = the PS_* constants; RT_PS_WORK / RT_PS_STALL / RT_PS_LEAVE / RT_PS_DESCEND override them for sweeps)
+struct PsTune {
+    int work, stall, leave, descend;
+};
 
 struct PsCounters {
     unsigned long long next_path, total_paths, rays;
@@ -123,9 +129,9 @@ enum { PSS_SHADE_PHASES, PSS_SHADE_ACT, PSS_SHADE_DONE, PSS_SHADE_ONPARK, PSS_EX
        PSS_LEAF_LANES, PSS_LEAF_PRIMS, PSS_EXT_ROUNDS, PSS_EXT_TRAV_LANES, PSS_NOISE, PSS_COUNT };
 
 template <bool STATS>
-__global__ void __launch_bounds__(PS_THREADS) persist_kernel(DSceneView S, DCamera cam, DRenderParams P, PsCounters* __restrict__ ctr,
+__global__ void __launch_bounds__(PS_THREADS, STATS ? 4 : PS_MIN_BLOCKS) persist_kernel(DSceneView S, DCamera cam, DRenderParams P, PsCounters* __restrict__ ctr,
                                                              float* __restrict__ accum, unsigned long long* __restrict__ rays_out,
-                                                             unsigned int chunk_size, unsigned long long* __restrict__ stats) {
+                                                             unsigned int chunk_size, unsigned long long* __restrict__ stats, PsTune tune) {
     unsigned int st_[PSS_COUNT];
     if (STATS)
         for (int k = 0; k < PSS_COUNT; ++k) st_[k] = 0u;
@@ -147,7 +153,8 @@ __global__ void __launch_bounds__(PS_THREADS) persist_kernel(DSceneView S, DCame
     park[17][threadIdx.x] = __int_as_float(ST_EMPTY);
     int park_status = ST_EMPTY;  // mirror of park[17] in a register
     int stack[RTB_BVH_STACK];
-    V3 inv = v3(0.f, 0.f, 0.f);
+    NodeRay nr;
+    nr.inv = nr.noi = v3(0.f, 0.f, 0.f), nr.pad = 0.f;
     // warp-uniform reservation of camera-path numbers
     unsigned long long chunk_next = 0, chunk_end = 0;
     uint32_t chunk_pixel = 0, chunk_sample = 0;  // (pixel, sample) of path chunk_next
@@ -165,7 +172,9 @@ __global__ void __launch_bounds__(PS_THREADS) persist_kernel(DSceneView S, DCame
             if (p.status == ST_READY) {
                 p.status = ST_TRAV;
                 p.cur = root_link, p.sp = 0;
-                inv = v3(1.0f / p.dx, 1.0f / p.dy, 1.0f / p.dz);
+                Ray r0;
+                r0.o = v3(p.ox, p.oy, p.oz), r0.d = v3(p.dx, p.dy, p.dz);
+                nr = node_ray(r0);
             }
         }
         const bool trav = p.status == ST_TRAV;
@@ -175,14 +184,14 @@ __global__ void __launch_bounds__(PS_THREADS) persist_kernel(DSceneView S, DCame
         const unsigned int m_work = __ballot_sync(0xffffffffu, p_work || k_work);
         if ((m_trav | m_work) == 0u) break;
 
-        if (m_work && (m_trav == 0u || __popc(m_work) >= PS_WORK || __popc(m_work & ~m_trav) >= PS_STALL)) {
+        if (m_work && (m_trav == 0u || __popc(m_work) >= tune.work || __popc(m_work & ~m_trav) >= tune.stall)) {
             // ================================================================ shade / regenerate phase
             const bool act = p_work || k_work;
             const bool on_park = act && !p_work;  // the register path is busy traversing: work on the parked one
             PS_STAT(PSS_SHADE_PHASES, 1)
             PS_STAT(PSS_SHADE_ACT, __popc(m_work))
             PS_STAT(PSS_SHADE_ONPARK, __popc(__ballot_sync(0xffffffffu, on_park)))
-            if (on_park) {  // the traversing path waits in the parked record (its stack and `inv` stay where they are)
+            if (on_park) {  // the traversing path waits in the parked record (its stack and node-test constants stay where they are)
                 const int st = p.status;
                 park_swap(park, p);
                 park_status = st;
@@ -298,8 +307,8 @@ __global__ void __launch_bounds__(PS_THREADS) persist_kernel(DSceneView S, DCame
                 const char* base = reinterpret_cast<const char*>(S.nodes + cur);
                 float4 l0 = ld4(base), l1 = ld4(base + 16), r0 = ld4(base + 32), r1 = ld4(base + 48);
                 float tl, tr;
-                bool hl = slab_node(l0, l1, r.o, inv, RTB_T_MIN, t_best, tl);
-                bool hr = slab_node(r0, r1, r.o, inv, RTB_T_MIN, t_best, tr);
+                bool hl = slab_node(l0, l1, nr, RTB_T_MIN, t_best, tl);
+                bool hr = slab_node(r0, r1, nr, RTB_T_MIN, t_best, tr);
                 int ll = (int)as_uint(l0.w), lr = (int)as_uint(r0.w);
                 if (hl && hr) {
                     bool left_first = tl <= tr;
@@ -312,7 +321,7 @@ __global__ void __launch_bounds__(PS_THREADS) persist_kernel(DSceneView S, DCame
                 } else {
                     cur = sp > 0 ? stack[--sp] : PS_DONE;
                 }
-                if (__popc(__activemask()) < PS_MIN_DESCEND) break;
+                if (__popc(__activemask()) < tune.descend) break;
             }
             __syncwarp();
             // (b) one leaf: every primitive of it, then pop
@@ -341,7 +350,7 @@ __global__ void __launch_bounds__(PS_THREADS) persist_kernel(DSceneView S, DCame
             }
             const unsigned int busy = __ballot_sync(0xffffffffu, has);
             if (busy == 0u) break;
-            if (__popc(m_trav & ~busy) >= PS_LEAVE) break;
+            if (__popc(m_trav & ~busy) >= tune.leave) break;
         }
         p.cur = cur, p.sp = sp, p.t_best = t_best;
     }
@@ -396,11 +405,16 @@ int launch_persist(RtScene* s, const DCamera& cam, const RtParams* p, int begin,
         unsigned int chunk = (unsigned int)std::min<unsigned long long>(PS_CHUNK, std::max<unsigned long long>(32ull, per_warp));
         chunk = (unsigned int)std::min<unsigned long long>(chunk, std::max<unsigned long long>(1ull, npix));
         ps_reset_kernel<<<1, 1, 0, stream>>>(w->ctr, total);
+        PsTune tune = {PS_WORK, PS_STALL, PS_LEAVE, PS_MIN_DESCEND};
+        if (const char* e = getenv("RT_PS_WORK")) tune.work = atoi(e);
+        if (const char* e = getenv("RT_PS_STALL")) tune.stall = atoi(e);
+        if (const char* e = getenv("RT_PS_LEAVE")) tune.leave = atoi(e);
+        if (const char* e = getenv("RT_PS_DESCEND")) tune.descend = atoi(e);
         if (getenv("RT_PS_STATS")) {  // debug: phase statistics on stderr (slower kernel; never used by the bench)
             unsigned long long* d_stats = nullptr;
             CU_TRY(cudaMalloc(&d_stats, PSS_COUNT * sizeof(unsigned long long)));
             CU_TRY(cudaMemsetAsync(d_stats, 0, PSS_COUNT * sizeof(unsigned long long), stream));
-            persist_kernel<true><<<blocks, PS_THREADS, 0, stream>>>(s->view, cam, P, w->ctr, d_accum, s->d_rays, chunk, d_stats);
+            persist_kernel<true><<<blocks, PS_THREADS, 0, stream>>>(s->view, cam, P, w->ctr, d_accum, s->d_rays, chunk, d_stats, tune);
             unsigned long long h[PSS_COUNT];
             CU_TRY(cudaMemcpyAsync(h, d_stats, sizeof h, cudaMemcpyDeviceToHost, stream));
             CU_TRY(cudaStreamSynchronize(stream));
@@ -411,7 +425,7 @@ int launch_persist(RtScene* s, const DCamera& cam, const RtParams* p, int begin,
             for (int k = 0; k < PSS_COUNT; ++k) fprintf(stderr, " %s=%llu", names[k], h[k]);
             fprintf(stderr, "\n");
         } else {
-            persist_kernel<false><<<blocks, PS_THREADS, 0, stream>>>(s->view, cam, P, w->ctr, d_accum, s->d_rays, chunk, nullptr);
+            persist_kernel<false><<<blocks, PS_THREADS, 0, stream>>>(s->view, cam, P, w->ctr, d_accum, s->d_rays, chunk, nullptr, tune);
         }
         CU_TRY(cudaGetLastError());
         *launches += 2;

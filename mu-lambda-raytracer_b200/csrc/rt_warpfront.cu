@@ -95,7 +95,8 @@ __global__ void __launch_bounds__(WA_THREADS) warpfront_kernel(DSceneView S, DCa
         unsigned int my_slot = 0;
         Ray r;
         r.o = r.d = v3(0.f, 0.f, 0.f);
-        V3 inv = v3(0.f, 0.f, 0.f);
+        NodeRay nr;
+    nr.inv = nr.noi = v3(0.f, 0.f, 0.f), nr.pad = 0.f;
         float t_best = RTB_INF;
         int prim_best = -1, face_best = 0, mat_best = 0, origin_prim = -1, origin_face = 0, code_in = -1;
         // warp-uniform queue state
@@ -163,7 +164,7 @@ __global__ void __launch_bounds__(WA_THREADS) warpfront_kernel(DSceneView S, DCa
                     t_best = pool.f[F_T][my_slot], code_in = __float_as_int(pool.f[F_CODE][my_slot]);
                     origin_prim = __float_as_int(pool.f[F_ORG][my_slot]);
                     origin_face = (int)((__float_as_uint(pool.f[F_FLAGS][my_slot]) >> WF_FACE_SHIFT) & 7u);
-                    inv = v3(1.0f / r.d.x, 1.0f / r.d.y, 1.0f / r.d.z);
+                    nr = node_ray(r);
                     prim_best = -1, face_best = 0;
                     sp = 0, cur = root_link;
                     has = true;
@@ -232,8 +233,8 @@ __global__ void __launch_bounds__(WA_THREADS) warpfront_kernel(DSceneView S, DCa
                     const char* base = reinterpret_cast<const char*>(S.nodes + cur);
                     float4 l0 = ld4(base), l1 = ld4(base + 16), r0 = ld4(base + 32), r1 = ld4(base + 48);
                     float tl, tr;
-                    bool hl = slab_node(l0, l1, r.o, inv, RTB_T_MIN, t_best, tl);
-                    bool hr = slab_node(r0, r1, r.o, inv, RTB_T_MIN, t_best, tr);
+                    bool hl = slab_node(l0, l1, nr, RTB_T_MIN, t_best, tl);
+                    bool hr = slab_node(r0, r1, nr, RTB_T_MIN, t_best, tr);
                     int ll = (int)as_uint(l0.w), lr = (int)as_uint(r0.w);
                     if (hl && hr) {
                         bool left_first = tl <= tr;

@@ -113,7 +113,8 @@ __global__ void __launch_bounds__(WF_EXT_THREADS) wf_extend_kernel(DSceneView S,
     unsigned int slot = 0, flags = 0;
     Ray r;
     r.o = r.d = v3(0.f, 0.f, 0.f);
-    V3 inv = v3(0.f, 0.f, 0.f);
+    NodeRay nr;
+    nr.inv = nr.noi = v3(0.f, 0.f, 0.f), nr.pad = 0.f;
     float t_best = RTB_INF;
     int prim_best = -1, face_best = 0, mat_best = 0, origin_prim = -1, code_in = -1;
     const int root_link = S.n_prims > 0 ? (int)as_uint(ld4(S.nodes).w) : WF_DONE;
@@ -176,7 +177,7 @@ __global__ void __launch_bounds__(WF_EXT_THREADS) wf_extend_kernel(DSceneView S,
                 r.o = v3(a.x, a.y, a.z), r.d = v3(b.x, b.y, b.z);
                 flags = __float_as_uint(b.w);
                 t_best = d.x, code_in = __float_as_int(d.y), origin_prim = __float_as_int(d.z);
-                inv = v3(1.0f / r.d.x, 1.0f / r.d.y, 1.0f / r.d.z);
+                nr = node_ray(r);
                 prim_best = -1, face_best = 0;
                 sp = 0, cur = root_link;
                 has = true;
@@ -195,8 +196,8 @@ __global__ void __launch_bounds__(WF_EXT_THREADS) wf_extend_kernel(DSceneView S,
                 const char* base = reinterpret_cast<const char*>(S.nodes + cur);
                 float4 l0 = ld4(base), l1 = ld4(base + 16), r0 = ld4(base + 32), r1 = ld4(base + 48);
                 float tl, tr;
-                bool hl = slab_node(l0, l1, r.o, inv, RTB_T_MIN, t_best, tl);
-                bool hr = slab_node(r0, r1, r.o, inv, RTB_T_MIN, t_best, tr);
+                bool hl = slab_node(l0, l1, nr, RTB_T_MIN, t_best, tl);
+                bool hr = slab_node(r0, r1, nr, RTB_T_MIN, t_best, tr);
                 int ll = (int)as_uint(l0.w), lr = (int)as_uint(r0.w);
                 if (hl && hr) {
                     bool left_first = tl <= tr;

@@ -143,7 +143,9 @@ def compare_surface(g, o, rays, grazing=0.02, tol=1e-5):
     cos = np.abs(np.sum(dirn * o["normal"], axis=1))
     cos_g = np.abs(np.sum(dirn * g["normal"].astype(np.float64), axis=1))  # where only the device hit, judge grazing by ITS normal
     mism = ohit != ghit
-    hard = mism & ~(ohit & (cos < grazing)) & ~(ghit & ~ohit & (cos_g < grazing))
+    # ... or passes within f32 rounding of the primitive's rim (u or v at 0 or 1: the edge of a rect / box face)
+    rim = lambda h: (np.minimum(h["u"], 1.0 - h["u"]) < 2e-5) | (np.minimum(h["v"], 1.0 - h["v"]) < 2e-5)
+    hard = mism & ~(ohit & ((cos < grazing) | rim(o))) & ~(ghit & ~ohit & ((cos_g < grazing) | rim(g)))
     both = ohit & ghit & (cos >= grazing)
     scale = np.abs(rays[:, :3]).max(axis=1) + np.abs(o["t"]) * dlen + 1.0
     err = np.abs(g["t"].astype(np.float64) - o["t"]) * dlen / scale

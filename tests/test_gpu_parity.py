@@ -42,7 +42,9 @@ def check_hits(g, o, rays, grazing=0.02, tol=1e-5):
     cos_g = np.abs(np.sum(dirn * g["normal"].astype(np.float64), axis=1))  # where only the device hit, judge grazing by ITS normal
     mism = ohit != ghit
     # a miss/hit disagreement is tolerated only if the oracle's hit is grazing or sits at the very end of the range
-    hard = mism & ~(ohit & (cos < grazing)) & ~(ghit & ~ohit & (cos_g < grazing))
+    # ... or passes within f32 rounding of the primitive's rim (u or v at 0 or 1: the edge of a rect / box face)
+    rim = lambda h: (np.minimum(h["u"], 1.0 - h["u"]) < 2e-5) | (np.minimum(h["v"], 1.0 - h["v"]) < 2e-5)
+    hard = mism & ~(ohit & ((cos < grazing) | rim(o))) & ~(ghit & ~ohit & ((cos_g < grazing) | rim(g)))
     assert hard.sum() <= max(2, len(rays) // 100000), f"{hard.sum()} hit/miss mismatches outside the grazing band"
     both = ohit & ghit & (cos >= grazing)
     scale = np.abs(rays[:, :3]).max(axis=1) + np.abs(o["t"]) * dlen + 1.0
