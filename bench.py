@@ -32,6 +32,10 @@ WORLD, SEED, WIDTH, HEIGHT, ASPECT, MAX_DEPTH, JOB_SPP = "final_scene", 42, 800,
 # Algorithmic work of the REFERENCE's traversal per camera path on C4, counted by the oracle's instrumentation
 # (tools/algo_work.py: 800x800, 16 spp, seed 42).  flops = 27*aabb + 45*sphere + 15*rect + 12*xform
 # + 40*medium + shade terms; bytes = 32 B per node / primitive record touched.
+# DRAM bytes per camera path of the dominant kernel, from the committed ncu --set full captures (profiles/): C4 at 64 spp,
+# dram__bytes_read.sum + dram__bytes_write.sum of one launch divided by the paths of that launch
+NCU_DRAM_BYTES_PER_PATH = {"persistent": 10.78e6 / 40.96e6, "megakernel": 10.56e6 / 40.96e6, "wavefront": 597e6 / 504e3}
+
 ALGO = {"rays_per_path": 4.159, "aabb": 66.59, "sphere": 42.99, "rect": 60.77, "xform": 8.318, "medium": 8.318,
         "lambertian": 0.878, "metal": 0.0312, "dielectric": 0.315, "isotropic": 1.963, "perlin": 0.0682, "image": 0.0695,
         "background": 0.886}  # tools/algo_work.py 16 (frozen in BASELINE.md section 4)
@@ -239,15 +243,18 @@ def run_b200(args):
         barrier()
         t0 = time.perf_counter()
         for k in range(args.e2e_steps):
-            sc = rt.Scene(desc, device=local_rank)  # flatten + BVH build + H2D upload of the scene
+            sc = rt.Scene(desc, device=local_rank)  # rt_scene_create: flatten + BVH build + H2D upload of the scene
             pk = params(300000 + k)
-            abi.check(lib.rt_render_accumulate_device(sc.handle, C.byref(cam.c), C.byref(pk), accum.zero_().data_ptr(), stream.cuda_stream, None))
-            if dist is not None:
+            if dist is None:
+                # one GPU: the reference-facing call itself, Renderer::render with HOST buffers (rt_render)
+                abi.check(lib.rt_render(sc.handle, C.byref(cam.c), C.byref(pk), None, host_rgb.data_ptr(), abi.RtProgressFn(), None, None))
+            else:
+                abi.check(lib.rt_render_accumulate_device(sc.handle, C.byref(cam.c), C.byref(pk), accum.zero_().data_ptr(), stream.cuda_stream, None))
                 dist.reduce(accum, dst=0, op=dist.ReduceOp.SUM)
-            if rank == 0:
-                abi.check(lib.rt_tonemap_device(accum.data_ptr(), rgb.data_ptr(), WIDTH * HEIGHT, total_spp, local_rank, stream.cuda_stream))
-                host_rgb.copy_(rgb, non_blocking=True)
-            torch.cuda.synchronize()
+                if rank == 0:
+                    abi.check(lib.rt_tonemap_device(accum.data_ptr(), rgb.data_ptr(), WIDTH * HEIGHT, total_spp, local_rank, stream.cuda_stream))
+                    host_rgb.copy_(rgb, non_blocking=True)
+                torch.cuda.synchronize()
             sc.close()
         barrier()
         dt = time.perf_counter() - t0
@@ -256,7 +263,8 @@ def run_b200(args):
             dist.all_reduce(tt, op=dist.ReduceOp.MAX)
         e2e = {"value": paths_per_step * args.e2e_steps / float(tt.item()) / 1e6, "unit": "Mpaths/s",
                "h2d_bytes_per_step": int(scene_bytes) * world_size, "d2h_bytes_per_step": int(host_rgb.numel() * 4),
-               "api": "Scene(desc) [flatten+BVH+upload] -> rt_render_accumulate_device -> reduce -> rt_tonemap_device -> pinned host rgb",
+               "api": ("rt_scene_create [flatten+BVH+upload] -> rt_render(host rgb buffer) -> rt_scene_destroy" if dist is None else
+                       "rt_scene_create -> rt_render_accumulate_device -> ncclReduce -> rt_tonemap_device -> pinned host rgb"),
                "steps": args.e2e_steps}
 
     cpu = None
@@ -285,7 +293,9 @@ def run_b200(args):
             "e2e": e2e,
             "gpu_launches": int(launches[0]) * args.steps,
             "roofline": {"bound": "fp32", "achieved": achieved, "peak": fp32_peak, "unit": "TFLOP/s", "frac": achieved / fp32_peak,
-                         "traffic": None, "kernel": kernels, "kernel_ms": render_ms, "kernel_launches": st.kernel_launches,
+                         "traffic": (NCU_DRAM_BYTES_PER_PATH[pipeline_used] * WIDTH * HEIGHT * spp if pipeline_used in NCU_DRAM_BYTES_PER_PATH else None),
+                         "traffic_note": "bytes per step = ncu dram bytes per path (profiles/, 64-spp capture) x paths per step",
+                         "kernel": kernels, "kernel_ms": render_ms, "kernel_launches": st.kernel_launches,
                          "paths_per_kernel_ms": WIDTH * HEIGHT * spp,
                          "algorithmic_flops_per_path": algo_flops_per_path(), "algorithmic_bytes_per_path": algo_bytes_per_path(),
                          "peak_source": f"{n_sm} SMs x 128 lanes x 2 x sm_max_mhz from MEASURED_PEAKS.json ({how}); no measured FP32 peak exists",

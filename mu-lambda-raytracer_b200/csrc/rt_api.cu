@@ -427,6 +427,8 @@ int rt_intersect_batch(const RtScene* scene, int32_t node, const float* rays, in
         if (rc != RT_OK) return rc;
         target = sub;
         mode = scene->desc->d.nodes[node].kind == RT_NODE_MEDIUM ? QUERY_MEDIUM : QUERY_LINEAR;
+    } else if (node >= 0 && scene->desc && scene->desc->d.nodes[node].kind == RT_NODE_MEDIUM) {
+        mode = QUERY_MEDIUM;  // the root itself is a medium: its clipped boundary interval, as documented in the header
     }
     float* d_rays = nullptr;
     RtHit* d_out = nullptr;

@@ -1,5 +1,5 @@
 #!/bin/bash
-# one GPU-box visit: parity tests, the bench line, the reference arm, the ncu launch list and one full capture per hot kernel
+# one GPU-box visit: parity tests, the bench line, the reference arm, the ncu launch list and one full capture of the hot kernel
 set -u
 TAG=${1:-r1}
 mkdir -p gpurun_out
@@ -10,6 +10,5 @@ CMD="python bench.py --steps 1 --warmup 1 --spp 64 --e2e-steps 0 --cpu-spp 0"
 $CMD > gpurun_out/plain_$TAG.log 2>&1 && \
 ncu --metrics gpu__time_duration.sum --clock-control none -c 600 --csv --log-file gpurun_out/launches_$TAG.csv $CMD > gpurun_out/ncu_launch_$TAG.log 2>&1
 echo launches_rc=$?
-ncu --set full --clock-control none --import-source on -k regex:wf_extend -s 30 -c 1 -f -o gpurun_out/prof_extend_$TAG $CMD > gpurun_out/ncu_full_extend_$TAG.log 2>&1; echo extend_rc=$?
-ncu --set full --clock-control none --import-source on -k regex:wf_shade -s 30 -c 1 -f -o gpurun_out/prof_shade_$TAG $CMD > gpurun_out/ncu_full_shade_$TAG.log 2>&1; echo shade_rc=$?
+ncu --set full --clock-control none --import-source on -k regex:persist_kernel -s 1 -c 1 -f -o gpurun_out/prof_persist_$TAG $CMD > gpurun_out/ncu_full_persist_$TAG.log 2>&1; echo persist_rc=$?
 cat gpurun_out/bench_$TAG.json
