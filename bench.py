@@ -170,6 +170,7 @@ def run_b200(args):
         p.seed = SEED
         # disjoint Philox sample indices per rank and per step
         p.sample_begin, p.sample_count = (step * world_size + rank) * spp, spp
+        assert p.sample_begin + spp < 2 ** 31
         p.pipeline, p.device, p.samples_per_item = pipeline, -1, args.samples_per_item
         return p
 
@@ -201,7 +202,7 @@ def run_b200(args):
         torch.cuda.synchronize()
 
     for w in range(args.warmup):
-        step(100000 + w, count_stats=(w == 0))
+        step(1000 + w, count_stats=(w == 0))
     barrier()
     sampler = ClockSampler(local_rank) if rank == 0 else None
     if sampler:
@@ -223,7 +224,7 @@ def run_b200(args):
 
     # ---- the render region alone (CUDA events recorded by the library on the launching stream around ALL kernels of the
     # pipeline; no flush / reduce / tonemap): the numerator of the roofline figure
-    p = params(200000)
+    p = params(2000)
     st = abi.RtStats()
     accum.zero_()
     torch.cuda.synchronize()
@@ -244,7 +245,7 @@ def run_b200(args):
         t0 = time.perf_counter()
         for k in range(args.e2e_steps):
             sc = rt.Scene(desc, device=local_rank)  # rt_scene_create: flatten + BVH build + H2D upload of the scene
-            pk = params(300000 + k)
+            pk = params(3000 + k)
             if dist is None:
                 # one GPU: the reference-facing call itself, Renderer::render with HOST buffers (rt_render)
                 abi.check(lib.rt_render(sc.handle, C.byref(cam.c), C.byref(pk), None, host_rgb.data_ptr(), abi.RtProgressFn(), None, None))

@@ -11,6 +11,7 @@
 
 #include <algorithm>
 #include <cmath>
+#include <cstdlib>
 #include <cstring>
 #include <limits>
 #include <map>
@@ -299,7 +300,7 @@ class Flattener {
 
     // ---- SAH BVH over prim_box ----
     std::vector<int> order;
-    static constexpr int kMaxLeaf = 4;
+    int kMaxLeaf = 4;  // RT_BVH_MAX_LEAF overrides (tuning)
 
     Box3 bounds_of(int begin, int end) const {
         Box3 b;
@@ -353,6 +354,7 @@ class Flattener {
     }
 
     void build_bvh() {
+        if (const char* e = getenv("RT_BVH_MAX_LEAF")) kMaxLeaf = std::max(1, std::min(8, atoi(e)));
         int n = (int)out.prims.size();
         out.nodes.clear();
         out.nodes.push_back(DNode{});
