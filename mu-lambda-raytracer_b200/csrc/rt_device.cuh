@@ -365,6 +365,22 @@ RTB_DEV bool slab_node(const float4& n0, const float4& n1, const NodeRay& q, flo
     return tn <= fmaf(tf, 1.0000004f, q.pad);  // conservative: relative slack for the roundings of t, `pad` for those of o*inv
 }
 
+// Traversal stack entry: a node link and the entry distance of its box.  A popped entry whose box starts beyond the
+// closest hit found since it was pushed is dropped without fetching the node (same conservative bound as slab_node).
+#define RTB_TRAVERSAL_DONE ((int)0x80000000)
+struct alignas(8) StackEntry {
+    int node;
+    float tn;
+};
+RTB_DEV int stack_pop(const StackEntry* stack, int& sp, float t_best, float pad) {
+    const float limit = fmaf(t_best, 1.0000004f, pad);
+    while (sp > 0) {
+        const StackEntry e = stack[--sp];
+        if (e.tn <= limit) return e.node;
+    }
+    return RTB_TRAVERSAL_DONE;
+}
+
 // Closest surface hit with t in [tmin, +inf): replaces HittableList::hit + BHV::hit + the shapes.
 // origin_prim/origin_face identify the primitive the ray starts on (-1 for camera and medium rays).
 RTB_DEV void closest_hit(const DSceneView& S, const Ray& r, float tmin, float tmax, int origin_prim, int origin_face, float& t_best, int& prim_best,
@@ -372,10 +388,10 @@ RTB_DEV void closest_hit(const DSceneView& S, const Ray& r, float tmin, float tm
     t_best = tmax, prim_best = -1, face_best = 0;
     if (S.n_prims == 0) return;
     const NodeRay nr = node_ray(r);
-    int stack[RTB_BVH_STACK];
+    StackEntry stack[RTB_BVH_STACK];
     int sp = 0;
     int cur = (int)as_uint(ld4(S.nodes).w);  // link of the root (its own box is never tested)
-    for (;;) {
+    while (cur != RTB_TRAVERSAL_DONE) {
         if (cur < 0) {
             int v = ~cur;
             int first = v & 0xFFFFFF, count = v >> 24;
@@ -385,8 +401,7 @@ RTB_DEV void closest_hit(const DSceneView& S, const Ray& r, float tmin, float tm
                 int face;
                 if (hit_prim(S, p, r, tmin, t_best, i == origin_prim, origin_face, t, face)) t_best = t, prim_best = i, face_best = face;
             }
-            if (sp == 0) break;
-            cur = stack[--sp];
+            cur = stack_pop(stack, sp, t_best, nr.pad);
         } else {
             const char* base = reinterpret_cast<const char*>(S.nodes + cur);
             float4 l0 = ld4(base), l1 = ld4(base + 16), r0 = ld4(base + 32), r1 = ld4(base + 48);
@@ -396,15 +411,15 @@ RTB_DEV void closest_hit(const DSceneView& S, const Ray& r, float tmin, float tm
             int ll = (int)as_uint(l0.w), lr = (int)as_uint(r0.w);
             if (hl && hr) {
                 bool left_first = tl <= tr;
-                stack[sp++] = left_first ? lr : ll;
+                stack[sp].node = left_first ? lr : ll, stack[sp].tn = left_first ? tr : tl;
+                sp += 1;
                 cur = left_first ? ll : lr;
             } else if (hl) {
                 cur = ll;
             } else if (hr) {
                 cur = lr;
             } else {
-                if (sp == 0) break;
-                cur = stack[--sp];
+                cur = stack_pop(stack, sp, t_best, nr.pad);
             }
         }
     }

@@ -2,15 +2,15 @@
 // pool in registers + shared memory and warp ballots deciding which stage a warp executes next.
 //
 // It replaces Renderer::render / render_pixel / trace_internal (src/raytrace.rs:172-198, :79-101).  Every lane owns TWO
-// camera paths: one in registers (being traversed) and one parked in shared memory (waiting to be shaded, or
-// holding a fresh ray).  The warp alternates between
+// camera paths, both as records in shared memory; registers hold the context of the one being traversed (ray, closest
+// hit so far, cursor), the other waits to be shaded or holds a fresh ray.  The warp alternates between
 //   extend  : while-while BVH traversal of the register paths (32-byte nodes, 128-bit __ldg, short stack); lanes vote
 //             between the inner-node loop and a leaf step, exactly like wf_extend_kernel;
 //   shade   : when enough lanes hold a finished traversal (or an empty slot), those paths are shaded together —
 //             scatter / emit / background, terminated paths deposit beta * radiance with float REDs and are
 //             regenerated in place from a global camera-path counter (reserved in chunks, one atomic per 256 paths),
 //             the media event of the new ray is pre-sampled — and become "ready" again.
-// A lane whose register path finishes simply swaps it with its parked ready path and keeps traversing, so the extend
+// A lane whose traversal finishes simply starts on its other, ready path and keeps traversing, so the extend
 // stage runs with (nearly) full warps and the shade stage with (nearly) full warps, without any queue in global memory:
 // HBM only sees the accumulation REDs.  Noise textures are evaluated warp-cooperatively (the 56 gradient terms of
 // the 7-octave turbulence are spread over the lanes) instead of by one lane while 31 wait.
@@ -26,12 +26,15 @@
 namespace rtb {
 
 #define PS_THREADS 128
-#define PS_DONE ((int)0x80000000)
+#define PS_DONE RTB_TRAVERSAL_DONE
 #define PS_MIN_DESCEND 6   // lanes that must still be descending inner nodes for the inner loop to keep going
 #define PS_LEAVE 8         // lanes that must have finished before the warp leaves the traversal loop to swap paths
-#define PS_WORK 24         // lanes with shading / regeneration work pending that trigger a shade phase ...
+#define PS_WORK 28         // lanes with shading / regeneration work pending that trigger a shade phase ...
 #define PS_STALL 14        // ... or lanes that cannot traverse at all (both of their paths wait for the shade phase)
 #define PS_MIN_BLOCKS 5    // resident blocks per SM the kernel is compiled for: 96 registers, no spills (6/7/8 blocks spill and measured 4/6/11 % slower)
+#ifndef PS_SPECULATE
+#define PS_SPECULATE 0  // speculative descent (postponed leaves): evaluated, 1-6 % slower on C4 with one-primitive leaves
+#endif
 #define PS_CHUNK 256u      // camera paths a warp reserves per atomic
 
 enum { ST_EMPTY = 0, ST_TRAV = 1, ST_DONE = 2, ST_READY = 3 };
@@ -50,48 +53,40 @@ struct PersistState {
     int blocks = 0;
 };
 
-// one camera path of a lane.  hit: -1 miss, prim | face << 24 surface, WF_MEDIUM | m medium (as in WfSlot.D.y);
-// flags: depth left | origin face << 16 (as in WfSlot.B.w)
-struct LanePath {
-    float ox, oy, oz, dx, dy, dz;
-    float br, bg, bb;
-    float t_best;
-    uint32_t pixel, sample, flags;
-    int origin_prim, hit, cur, sp, status;
-};
-#define PS_WORDS 18
+// One camera path = one record of PS_REC words in shared memory, SoA over the block's threads (conflict-free):
+//   origin.xyz, direction.xyz, beta.rgb, t, pixel, sample, flags (depth left | origin face << 16), origin primitive, hit
+// hit: -1 miss, prim | face << 24 surface, WF_MEDIUM | m medium (as in WfSlot.D.y).  Every lane owns PS_SLOTS records;
+// the slot statuses live in one register (2 bits per slot).  Registers hold only the context of the traversal in
+// flight (ray, node-test constants, closest hit so far, cursor), so shading a parked path moves nothing around.
+enum { R_OX, R_OY, R_OZ, R_DX, R_DY, R_DZ, R_BR, R_BG, R_BB, R_T, R_PIXEL, R_SAMPLE, R_FLAGS, R_ORIGIN, R_HIT, PS_REC };
+#define PS_SLOTS 2
+typedef float PsPool[PS_SLOTS][PS_REC][PS_THREADS];
 
-__device__ __forceinline__ void park_swap(float (*park)[PS_THREADS], LanePath& p) {
+__device__ __forceinline__ int slot_status(unsigned int stat, int s) { return (int)((stat >> (2 * s)) & 3u); }
+__device__ __forceinline__ unsigned int slot_set(unsigned int stat, int s, int st) { return (stat & ~(3u << (2 * s))) | ((unsigned int)st << (2 * s)); }
+__device__ __forceinline__ int slot_find(unsigned int stat, int want) {  // lowest slot with that status, -1 if none
+    int found = -1;
+#pragma unroll
+    for (int s = PS_SLOTS - 1; s >= 0; --s)
+        if (slot_status(stat, s) == want) found = s;
+    return found;
+}
+
+__device__ __forceinline__ void rec_load(const PsPool& pool, int slot, WfSlot& s) {
     const unsigned int t = threadIdx.x;
-#define SWAPF(k, field)           \
-    {                             \
-        float tmp = park[k][t];   \
-        park[k][t] = p.field;     \
-        p.field = tmp;            \
-    }
-#define SWAPI(k, field)                                  \
-    {                                                    \
-        float tmp = park[k][t];                          \
-        park[k][t] = __int_as_float((int)p.field);       \
-        p.field = (decltype(p.field))__float_as_int(tmp); \
-    }
-    SWAPF(0, ox) SWAPF(1, oy) SWAPF(2, oz) SWAPF(3, dx) SWAPF(4, dy) SWAPF(5, dz) SWAPF(6, br) SWAPF(7, bg) SWAPF(8, bb) SWAPF(9, t_best)
-    SWAPI(10, pixel) SWAPI(11, sample) SWAPI(12, flags) SWAPI(13, origin_prim) SWAPI(14, hit) SWAPI(15, cur) SWAPI(16, sp) SWAPI(17, status)
-#undef SWAPF
-#undef SWAPI
+    const float(*r)[PS_THREADS] = pool[slot];
+    s.A = f4(r[R_OX][t], r[R_OY][t], r[R_OZ][t], r[R_PIXEL][t]);
+    s.B = f4(r[R_DX][t], r[R_DY][t], r[R_DZ][t], r[R_FLAGS][t]);
+    s.C = f4(r[R_BR][t], r[R_BG][t], r[R_BB][t], r[R_SAMPLE][t]);
+    s.D = f4(r[R_T][t], r[R_HIT][t], r[R_ORIGIN][t], 0.f);
 }
-
-__device__ __forceinline__ void to_slot(const LanePath& p, WfSlot& s) {
-    s.A = f4(p.ox, p.oy, p.oz, __uint_as_float(p.pixel));
-    s.B = f4(p.dx, p.dy, p.dz, __uint_as_float(p.flags));
-    s.C = f4(p.br, p.bg, p.bb, __uint_as_float(p.sample));
-    s.D = f4(p.t_best, __int_as_float(p.hit), __int_as_float(p.origin_prim), 0.f);
-}
-__device__ __forceinline__ void from_slot(const WfSlot& s, LanePath& p) {
-    p.ox = s.A.x, p.oy = s.A.y, p.oz = s.A.z, p.pixel = __float_as_uint(s.A.w);
-    p.dx = s.B.x, p.dy = s.B.y, p.dz = s.B.z, p.flags = __float_as_uint(s.B.w);
-    p.br = s.C.x, p.bg = s.C.y, p.bb = s.C.z, p.sample = __float_as_uint(s.C.w);
-    p.t_best = s.D.x, p.hit = __float_as_int(s.D.y), p.origin_prim = __float_as_int(s.D.z);
+__device__ __forceinline__ void rec_store(PsPool& pool, int slot, const WfSlot& s) {
+    const unsigned int t = threadIdx.x;
+    float(*r)[PS_THREADS] = pool[slot];
+    r[R_OX][t] = s.A.x, r[R_OY][t] = s.A.y, r[R_OZ][t] = s.A.z, r[R_PIXEL][t] = s.A.w;
+    r[R_DX][t] = s.B.x, r[R_DY][t] = s.B.y, r[R_DZ][t] = s.B.z, r[R_FLAGS][t] = s.B.w;
+    r[R_BR][t] = s.C.x, r[R_BG][t] = s.C.y, r[R_BB][t] = s.C.z, r[R_SAMPLE][t] = s.C.w;
+    r[R_T][t] = s.D.x, r[R_HIT][t] = s.D.y, r[R_ORIGIN][t] = s.D.z;
 }
 
 // Perlin::turbulence (textures.rs:76-88, depth 7) of one point, computed by the whole warp: term = (octave, corner),
@@ -140,21 +135,24 @@ __global__ void __launch_bounds__(PS_THREADS, STATS ? 4 : PS_MIN_BLOCKS) persist
         const unsigned int v_ = (unsigned int)(v); \
         if (lane == 0) st_[k] += v_;               \
     }
-    __shared__ float park[PS_WORDS][PS_THREADS];
+    __shared__ PsPool pool;
     const unsigned int lane = threadIdx.x & 31u;
     const unsigned int lt_mask = (1u << lane) - 1u;
     const int root_link = S.n_prims > 0 ? (int)as_uint(ld4(S.nodes).w) : PS_DONE;
     const unsigned long long total = ctr->total_paths;
     const unsigned int npix = (unsigned int)P.width * (unsigned int)P.height;
 
-    LanePath p;  // the register path
-    p.ox = p.oy = p.oz = p.dx = p.dy = p.dz = 0.f, p.br = p.bg = p.bb = 0.f, p.t_best = 0.f;
-    p.pixel = p.sample = p.flags = 0u, p.origin_prim = -1, p.hit = -1, p.cur = PS_DONE, p.sp = 0, p.status = ST_EMPTY;
-    park[17][threadIdx.x] = __int_as_float(ST_EMPTY);
-    int park_status = ST_EMPTY;  // mirror of park[17] in a register
-    int stack[RTB_BVH_STACK];
+    unsigned int stat = 0u;  // every slot ST_EMPTY
+    // context of the traversal in flight (tslot < 0: none)
+    int tslot = -1;
+    Ray r;
+    r.o = r.d = v3(0.f, 0.f, 0.f);
     NodeRay nr;
     nr.inv = nr.noi = v3(0.f, 0.f, 0.f), nr.pad = 0.f;
+    float t_best = 0.f;
+    int hit = -1, origin_prim = -1, origin_face = 0, cur = PS_DONE, sp = 0;
+    int pend = 0;  // a leaf reached but not tested yet (leaf links are negative, 0 = none): see the extend phase
+    StackEntry stack[RTB_BVH_STACK];  // (node link, entry distance of its box): see stack_pop
     // warp-uniform reservation of camera-path numbers
     unsigned long long chunk_next = 0, chunk_end = 0;
     uint32_t chunk_pixel = 0, chunk_sample = 0;  // (pixel, sample) of path chunk_next
@@ -162,51 +160,47 @@ __global__ void __launch_bounds__(PS_THREADS, STATS ? 4 : PS_MIN_BLOCKS) persist
     unsigned int n_rays = 0;
 
     for (;;) {
-        // ---- (1) a lane whose register path cannot traverse takes its parked ready path; a ready path starts traversing
-        if (p.status != ST_TRAV) {
-            if (p.status != ST_READY && park_status == ST_READY) {
-                const int st = p.status;
-                park_swap(park, p);  // p.status <- READY, park <- st
-                park_status = st;
-            }
-            if (p.status == ST_READY) {
-                p.status = ST_TRAV;
-                p.cur = root_link, p.sp = 0;
-                Ray r0;
-                r0.o = v3(p.ox, p.oy, p.oz), r0.d = v3(p.dx, p.dy, p.dz);
-                nr = node_ray(r0);
+        // ---- (1) an idle lane starts traversing one of its ready paths
+        if (tslot < 0) {
+            const int sl = slot_find(stat, ST_READY);
+            if (sl >= 0) {
+                const unsigned int t = threadIdx.x;
+                const float(*q)[PS_THREADS] = pool[sl];
+                r.o = v3(q[R_OX][t], q[R_OY][t], q[R_OZ][t]), r.d = v3(q[R_DX][t], q[R_DY][t], q[R_DZ][t]);
+                t_best = q[R_T][t], hit = __float_as_int(q[R_HIT][t]), origin_prim = __float_as_int(q[R_ORIGIN][t]);
+                origin_face = (int)((__float_as_uint(q[R_FLAGS][t]) >> WF_FACE_SHIFT) & 7u);
+                nr = node_ray(r);
+                cur = root_link, sp = 0, pend = 0;
+                tslot = sl;
+                stat = slot_set(stat, sl, ST_TRAV);
             }
         }
-        const bool trav = p.status == ST_TRAV;
-        const bool p_work = p.status == ST_DONE || (p.status == ST_EMPTY && !exhausted);
-        const bool k_work = park_status == ST_DONE || (park_status == ST_EMPTY && !exhausted);
+        const bool trav = tslot >= 0;
+        const int s_done = slot_find(stat, ST_DONE);
+        const int s_work = s_done >= 0 ? s_done : (exhausted ? -1 : slot_find(stat, ST_EMPTY));
         const unsigned int m_trav = __ballot_sync(0xffffffffu, trav);
-        const unsigned int m_work = __ballot_sync(0xffffffffu, p_work || k_work);
+        const unsigned int m_work = __ballot_sync(0xffffffffu, s_work >= 0);
         if ((m_trav | m_work) == 0u) break;
 
         if (m_work && (m_trav == 0u || __popc(m_work) >= tune.work || __popc(m_work & ~m_trav) >= tune.stall)) {
             // ================================================================ shade / regenerate phase
-            const bool act = p_work || k_work;
-            const bool on_park = act && !p_work;  // the register path is busy traversing: work on the parked one
+            const bool act = s_work >= 0;
+            const bool shade = s_done >= 0;
             PS_STAT(PSS_SHADE_PHASES, 1)
             PS_STAT(PSS_SHADE_ACT, __popc(m_work))
-            PS_STAT(PSS_SHADE_ONPARK, __popc(__ballot_sync(0xffffffffu, on_park)))
-            if (on_park) {  // the traversing path waits in the parked record (its stack and node-test constants stay where they are)
-                const int st = p.status;
-                park_swap(park, p);
-                park_status = st;
-            }
+            PS_STAT(PSS_SHADE_ONPARK, __popc(m_work & m_trav))
+            PS_STAT(PSS_SHADE_DONE, __popc(__ballot_sync(0xffffffffu, shade)))
             bool alive = false;
             V3 radiance = v3(0.f, 0.f, 0.f);
             NoiseReq req;
             req.tex = -1, req.p = v3(0.f, 0.f, 0.f);
             int segment_next = 0;
+            uint32_t pixel_out = 0u;
             WfSlot s;
-            const bool shade = act && p.status == ST_DONE;
-            PS_STAT(PSS_SHADE_DONE, __popc(__ballot_sync(0xffffffffu, shade)))
             if (shade) {
                 n_rays += 1u;
-                to_slot(p, s);
+                rec_load(pool, s_work, s);
+                pixel_out = __float_as_uint(s.A.w);
                 alive = wf_shade_core(S, P, s, radiance, &req, segment_next);
             }
             // noise textures: one point at a time, all lanes on its 56 gradient terms
@@ -231,7 +225,7 @@ __global__ void __launch_bounds__(PS_THREADS, STATS ? 4 : PS_MIN_BLOCKS) persist
                 }
             }
             if (shade && !alive) {  // the path ended: beta * (emission | background | 0) -> its pixel
-                float* dst = accum + 3 * (size_t)p.pixel;
+                float* dst = accum + 3 * (size_t)pixel_out;
                 if (radiance.x != 0.f) atomicAdd(dst + 0, radiance.x);
                 if (radiance.y != 0.f) atomicAdd(dst + 1, radiance.y);
                 if (radiance.z != 0.f) atomicAdd(dst + 2, radiance.z);
@@ -274,26 +268,17 @@ __global__ void __launch_bounds__(PS_THREADS, STATS ? 4 : PS_MIN_BLOCKS) persist
             if (act) {
                 if (alive) {
                     wf_presample_media(S, P, s, segment_next);
-                    from_slot(s, p);
-                    p.status = ST_READY;
+                    rec_store(pool, s_work, s);
+                    stat = slot_set(stat, s_work, ST_READY);
                 } else {
-                    p.status = ST_EMPTY;
+                    stat = slot_set(stat, s_work, ST_EMPTY);
                 }
-            }
-            if (on_park) {  // the traversing path comes back
-                const int st = p.status;
-                park_swap(park, p);
-                park_status = st;
             }
             continue;
         }
 
         // ==================================================================== extend phase
-        Ray r;
-        r.o = v3(p.ox, p.oy, p.oz), r.d = v3(p.dx, p.dy, p.dz);
         bool has = trav;
-        int cur = p.cur, sp = p.sp;
-        float t_best = p.t_best;
         PS_STAT(PSS_EXT_PHASES, 1)
         for (;;) {
             PS_STAT(PSS_EXT_ROUNDS, 1)
@@ -312,47 +297,74 @@ __global__ void __launch_bounds__(PS_THREADS, STATS ? 4 : PS_MIN_BLOCKS) persist
                 int ll = (int)as_uint(l0.w), lr = (int)as_uint(r0.w);
                 if (hl && hr) {
                     bool left_first = tl <= tr;
-                    stack[sp++] = left_first ? lr : ll;
+                    stack[sp].node = left_first ? lr : ll, stack[sp].tn = left_first ? tr : tl;
+                    sp += 1;
                     cur = left_first ? ll : lr;
                 } else if (hl) {
                     cur = ll;
                 } else if (hr) {
                     cur = lr;
                 } else {
-                    cur = sp > 0 ? stack[--sp] : PS_DONE;
+                    cur = stack_pop(stack, sp, t_best, nr.pad);
                 }
+#if PS_SPECULATE
+                // speculative descent (Aila & Laine): the first leaf a lane reaches is postponed and the lane keeps
+                // descending with the next node of its stack, so that the inner-node loop and the leaf step both run
+                // with more lanes; the price is a few node visits the postponed hit would have culled
+                if (cur < 0 && cur != PS_DONE && pend == 0) {
+                    pend = cur;
+                    cur = stack_pop(stack, sp, t_best, nr.pad);
+                }
+#endif
                 if (__popc(__activemask()) < tune.descend) break;
             }
             __syncwarp();
-            // (b) one leaf: every primitive of it, then pop
+            // (b) one leaf per lane: every primitive of it
+#if PS_SPECULATE
+            const int leaf = has ? pend : 0;
+#else
+            const int leaf = (has && cur < 0 && cur != PS_DONE) ? cur : 0;
+#endif
             if (STATS) {
-                const unsigned int lm = __ballot_sync(0xffffffffu, has && cur < 0 && cur != PS_DONE);
+                const unsigned int lm = __ballot_sync(0xffffffffu, leaf != 0);
                 PS_STAT(PSS_LEAF_STEPS, lm != 0u)
                 PS_STAT(PSS_LEAF_LANES, __popc(lm))
             }
-            if (has && cur < 0 && cur != PS_DONE) {
-                int v = ~cur;
+            if (leaf != 0) {
+                int v = ~leaf;
                 int first = v & 0xFFFFFF, count = v >> 24;
                 if (STATS) st_[PSS_LEAF_PRIMS] += (unsigned int)count;
                 for (int i = first; i < first + count; ++i) {
                     PrimRec q = load_prim(S.prims + i);
                     float t;
                     int face;
-                    if (hit_prim(S, q, r, RTB_T_MIN, t_best, i == p.origin_prim, (int)((p.flags >> WF_FACE_SHIFT) & 7u), t, face))
-                        t_best = t, p.hit = i | (face << 24);  // closer than the pre-sampled medium event, which it replaces
+                    if (hit_prim(S, q, r, RTB_T_MIN, t_best, i == origin_prim, origin_face, t, face))
+                        t_best = t, hit = i | (face << 24);  // closer than the pre-sampled medium event, which it replaces
                 }
-                cur = sp > 0 ? stack[--sp] : PS_DONE;
+#if PS_SPECULATE
+                pend = 0;
+#else
+                cur = stack_pop(stack, sp, t_best, nr.pad);
+#endif
             }
+#if PS_SPECULATE
+            if (has && cur < 0 && cur != PS_DONE) {  // the lane stopped at a second leaf: it becomes the postponed one
+                pend = cur;
+                cur = stack_pop(stack, sp, t_best, nr.pad);
+            }
+#endif
             __syncwarp();
-            if (has && cur == PS_DONE) {  // traversal finished: the hit record is final
+            if (has && cur == PS_DONE && pend == 0) {  // traversal finished: the hit record goes back to the path's slot
                 has = false;
-                p.status = ST_DONE;
+                pool[tslot][R_T][threadIdx.x] = t_best;
+                pool[tslot][R_HIT][threadIdx.x] = __int_as_float(hit);
+                stat = slot_set(stat, tslot, ST_DONE);
+                tslot = -1;
             }
             const unsigned int busy = __ballot_sync(0xffffffffu, has);
             if (busy == 0u) break;
             if (__popc(m_trav & ~busy) >= tune.leave) break;
         }
-        p.cur = cur, p.sp = sp, p.t_best = t_best;
     }
 
     for (int off = 16; off > 0; off >>= 1) n_rays += __shfl_down_sync(0xffffffffu, n_rays, off);

@@ -31,7 +31,7 @@ namespace rtb {
 #define WA_K (WA_SLOTS / 32)
 #define WA_WARPS 4
 #define WA_THREADS (WA_WARPS * 32)
-#define WA_DONE ((int)0x80000000)
+#define WA_DONE RTB_TRAVERSAL_DONE
 #define WA_REFILL 8   // idle lanes before the warp leaves the traversal loop to refill them
 #define WA_FLUSH 16   // idle lanes (with nothing ready) before a partial class batch is shaded
 #define WA_MIN_DESCEND 8
@@ -89,7 +89,7 @@ __global__ void __launch_bounds__(WA_THREADS) warpfront_kernel(DSceneView S, DCa
         const int sample0 = P.sample_begin + first_sample;  // global index of the item's first sample
 
         // lane-parked traversal
-        int stack[RTB_BVH_STACK];
+        StackEntry stack[RTB_BVH_STACK];
         int sp = 0, cur = WA_DONE;
         bool has = false;
         unsigned int my_slot = 0;
@@ -238,14 +238,15 @@ __global__ void __launch_bounds__(WA_THREADS) warpfront_kernel(DSceneView S, DCa
                     int ll = (int)as_uint(l0.w), lr = (int)as_uint(r0.w);
                     if (hl && hr) {
                         bool left_first = tl <= tr;
-                        stack[sp++] = left_first ? lr : ll;
+                        stack[sp].node = left_first ? lr : ll, stack[sp].tn = left_first ? tr : tl;
+                        sp += 1;
                         cur = left_first ? ll : lr;
                     } else if (hl) {
                         cur = ll;
                     } else if (hr) {
                         cur = lr;
                     } else {
-                        cur = sp > 0 ? stack[--sp] : WA_DONE;
+                        cur = stack_pop(stack, sp, t_best, nr.pad);
                     }
                     if (__popc(__activemask()) < WA_MIN_DESCEND) break;
                 }
@@ -261,7 +262,7 @@ __global__ void __launch_bounds__(WA_THREADS) warpfront_kernel(DSceneView S, DCa
                         if (hit_prim(S, p, r, RTB_T_MIN, t_best, i == origin_prim, origin_face, t, face))
                             t_best = t, prim_best = i, face_best = face, mat_best = p.mat;
                     }
-                    cur = sp > 0 ? stack[--sp] : WA_DONE;
+                    cur = stack_pop(stack, sp, t_best, nr.pad);
                 }
                 __syncwarp();
                 const unsigned int working = __ballot_sync(0xffffffffu, has && cur != WA_DONE);

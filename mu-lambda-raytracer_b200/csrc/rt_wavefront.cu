@@ -60,7 +60,7 @@ struct WavefrontState {
 #define WF_EXT_THREADS 128
 #define WF_EXT_WARPS (WF_EXT_THREADS / 32)
 #define WF_SHADE_THREADS 256
-#define WF_DONE ((int)0x80000000)
+#define WF_DONE RTB_TRAVERSAL_DONE
 #define WF_REFILL 8       // lanes that must be idle before a warp stops traversing to retire / fetch rays
 #define WF_MIN_DESCEND 8  // lanes that must still be descending inner nodes for the inner loop to keep going
 #define WF_CHUNK 64       // queue entries a warp reserves per atomic
@@ -104,7 +104,7 @@ __global__ void __launch_bounds__(WF_EXT_THREADS) wf_extend_kernel(DSceneView S,
     if (lane <= WF_CLASSES) bin_count[warp][lane] = 0;
     __syncwarp();
 
-    int stack[RTB_BVH_STACK];
+    StackEntry stack[RTB_BVH_STACK];
     int sp = 0;
     int cur = WF_DONE;
     bool has = false;
@@ -201,14 +201,15 @@ __global__ void __launch_bounds__(WF_EXT_THREADS) wf_extend_kernel(DSceneView S,
                 int ll = (int)as_uint(l0.w), lr = (int)as_uint(r0.w);
                 if (hl && hr) {
                     bool left_first = tl <= tr;
-                    stack[sp++] = left_first ? lr : ll;
+                    stack[sp].node = left_first ? lr : ll, stack[sp].tn = left_first ? tr : tl;
+                    sp += 1;
                     cur = left_first ? ll : lr;
                 } else if (hl) {
                     cur = ll;
                 } else if (hr) {
                     cur = lr;
                 } else {
-                    cur = sp > 0 ? stack[--sp] : WF_DONE;
+                    cur = stack_pop(stack, sp, t_best, nr.pad);
                 }
                 if (__popc(__activemask()) < WF_MIN_DESCEND) break;  // too few lanes descending: let the others catch up
             }
@@ -224,7 +225,7 @@ __global__ void __launch_bounds__(WF_EXT_THREADS) wf_extend_kernel(DSceneView S,
                     if (hit_prim(S, p, r, RTB_T_MIN, t_best, i == origin_prim, (int)((flags >> WF_FACE_SHIFT) & 7u), t, face))
                         t_best = t, prim_best = i, face_best = face, mat_best = p.mat;
                 }
-                cur = sp > 0 ? stack[--sp] : WF_DONE;
+                cur = stack_pop(stack, sp, t_best, nr.pad);
             }
             __syncwarp();
             // (c) leave for retire/refill when enough lanes are idle, or when nothing is left to traverse
