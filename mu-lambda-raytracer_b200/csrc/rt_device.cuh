@@ -86,6 +86,9 @@ inline void image_fetch(const DImage& im, int i, int j, float rgb[3]) {
 
 namespace rtb {
 
+#ifndef RTB_USE_FFMA2
+#define RTB_USE_FFMA2 1
+#endif
 #define RTB_INF as_float(0x7f800000u)
 #define RTB_T_MIN 0.001f  // raytrace.rs:90, in units of the (unnormalised) direction
 
@@ -356,8 +359,15 @@ RTB_DEV NodeRay node_ray(const Ray& r) {
     return n;
 }
 RTB_DEV bool slab_node(const float4& n0, const float4& n1, const NodeRay& q, float tmin, float tmax, float& tn_out) {
+#if defined(__CUDA_ARCH__) && !defined(RTB_HOST_EMULATION) && RTB_USE_FFMA2
+    // sm_100 packed FP32: one FFMA2 issues the x and y slabs of a box corner together (same roundings as two FFMA)
+    const float2 ixy = make_float2(q.inv.x, q.inv.y), nxy = make_float2(q.noi.x, q.noi.y);
+    const float2 a2 = __ffma2_rn(make_float2(n0.x, n0.y), ixy, nxy), b2 = __ffma2_rn(make_float2(n1.x, n1.y), ixy, nxy);
+    const float ax = a2.x, ay = a2.y, bx = b2.x, by = b2.y;
+#else
     float ax = fmaf(n0.x, q.inv.x, q.noi.x), bx = fmaf(n1.x, q.inv.x, q.noi.x);
     float ay = fmaf(n0.y, q.inv.y, q.noi.y), by = fmaf(n1.y, q.inv.y, q.noi.y);
+#endif
     float az = fmaf(n0.z, q.inv.z, q.noi.z), bz = fmaf(n1.z, q.inv.z, q.noi.z);
     float tn = fmaxf(fmaxf(fminf(ax, bx), fminf(ay, by)), fmaxf(fminf(az, bz), tmin));
     float tf = fminf(fminf(fmaxf(ax, bx), fmaxf(ay, by)), fminf(fmaxf(az, bz), tmax));

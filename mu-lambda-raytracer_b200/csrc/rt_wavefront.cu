@@ -282,7 +282,7 @@ __device__ __forceinline__ unsigned int block_rank(bool flag, unsigned int* warp
 
 // Shade: one thread per queued path; blocks are class-uniform.  Two atomics per BLOCK: one reserves camera-path
 // numbers for the regenerated paths, one reserves the block's range of the next active queue.
-__global__ void __launch_bounds__(WF_SHADE_THREADS) wf_shade_kernel(DSceneView S, WfView W, int parity) {
+__global__ void __launch_bounds__(WF_SHADE_THREADS, 3) wf_shade_kernel(DSceneView S, WfView W, int parity) {
     __shared__ unsigned int warp_sums[WF_SHADE_THREADS / 32];
     __shared__ unsigned long long path_base;
     __shared__ unsigned int queue_base;
