@@ -159,3 +159,80 @@ def test_wavefront_many_rounds_small_pool(monkeypatch):
         close = np.isclose(res["megakernel"][0], res[other][0], rtol=1e-4, atol=1e-3).all(axis=2)
         assert close.mean() > 0.97, (other, close.mean())
     scene.close()
+
+
+@pytest.mark.parametrize("W,H,spp,depth", [(2, 2, 1, 50), (7, 5, 3, 50), (33, 17, 2, 1), (16, 16, 4, 0), (40, 24, 5, 3)])
+def test_edge_sizes_and_depths_all_pipelines(W, H, spp, depth):
+    """tiny and ragged images, one sample, max_depth 1 (camera ray only) and 0 (every path is Color::ZERO at once,
+    raytrace.rs:87-89): every pipeline traces exactly W*H*spp paths and agrees with the megakernel"""
+    world = rt.World("final_scene")
+    desc = world.build(42)
+    scene = rt.Scene(desc)
+    info = world.camera()
+    cam = S.make_camera(info["lookfrom"], info["lookat"], info["field_of_view"], W / H)
+    out = {}
+    for pname, pid in PIPELINES.items():
+        r = rt.Renderer.new_with_rng(cam, scene, world.background(), rt.RenderingParams(spp, H, W), rt.RecursiveRayTracer(depth), rt.SeedableRngator(99))
+        r.pipeline = pid
+        rgb, accum = r.render_arrays()
+        assert r.stats["paths"] == W * H * spp
+        assert np.isfinite(accum).all() and (accum >= 0).all()
+        out[pname] = (accum.astype(np.float64), r.stats["rays"])
+    base, base_rays = out["megakernel"]
+    if depth == 0:
+        for a, rays in out.values():
+            assert rays == 0 and not a.any()
+    else:
+        assert base_rays >= W * H * spp
+        for pname, (a, rays) in out.items():
+            assert abs(int(rays) - int(base_rays)) <= max(2, 0.01 * base_rays), pname
+            close = np.isclose(a, base, rtol=1e-4, atol=1e-4 * max(base.mean(), 1e-6)).all(axis=2)
+            assert close.mean() >= 0.95, (pname, close.mean())
+    scene.close()
+
+
+def test_same_seed_same_image_different_seed_different_image():
+    world = rt.World("cornell_smoke")
+    scene = rt.Scene(world.build(0))
+    info = world.camera()
+    cam = S.make_camera(info["lookfrom"], info["lookat"], info["field_of_view"], 1.0)
+
+    def render(seed):
+        r = rt.Renderer.new_with_rng(cam, scene, world.background(), rt.RenderingParams(8, 48, 48), rt.RecursiveRayTracer(50), rt.SeedableRngator(seed))
+        _, accum = r.render_arrays()
+        return accum.astype(np.float64), r.stats["rays"]
+
+    a1, r1 = render(5)
+    a2, r2 = render(5)
+    b, _ = render(6)
+    assert r1 == r2  # the same Philox streams: the same paths, float sums differ only by the order of the REDs
+    assert np.allclose(a1, a2, rtol=1e-5, atol=1e-5)
+    assert not np.allclose(a1, b, rtol=1e-3, atol=1e-3)
+    scene.close()
+
+
+@pytest.mark.parametrize("name,aspect,kw", [("final_scene", 1.0, {}), ("random", 1.5, dict(aperture=0.1, focus_dist=10.0)), ("cornell_smoke", 1.0, {})])
+def test_no_bias_at_high_sample_count(name, aspect, kw):
+    """The RMSE criterion at 1024 spp, where Monte-Carlo noise is 4x smaller than in the 64-spp test and a bias of the
+    f32 device path (self-intersection, culling, sampler) would stand out of it: RMSE(device, oracle) must stay
+    within 1.1x the oracle's own seed-to-seed RMSE."""
+    world = rt.World(name)
+    scene = rt.Scene(world.build(42))
+    ow = S.OracleWorld(name, 42)
+    cam = S.make_camera(ow.lookfrom, ow.lookat, ow.vfov, aspect, **kw)
+    W, spp = 72, 1024
+    H = int(W / aspect)
+    r = rt.Renderer.new_with_rng(cam, scene, world.background(), rt.RenderingParams(spp, H, W), rt.RecursiveRayTracer(50), rt.SeedableRngator(4242))
+    _, accum = r.render_arrays()
+    a1, _, _, _ = ow.render(cam.c, W, H, spp, render_seed=1)
+    a2, _, _, _ = ow.render(cam.c, W, H, spp, render_seed=2)
+    disp = lambda a: np.sqrt(np.clip(a / spp, 0.0, 1.0))
+    rm = lambda x, y: float(np.sqrt(np.mean((x - y) ** 2)))
+    floor = rm(disp(a1), disp(a2))
+    g = disp(accum.astype(np.float64))
+    got = 0.5 * (rm(g, disp(a1)) + rm(g, disp(a2)))
+    assert got <= 1.1 * floor, f"{name}: RMSE {got:.5f} vs noise floor {floor:.5f} at {spp} spp"
+    # linear radiance, channel means: within 1 % of the oracle's
+    m_g, m_o = accum.reshape(-1, 3).mean(axis=0) / spp, 0.5 * (a1 + a2).reshape(-1, 3).mean(axis=0) / spp
+    assert np.all(np.abs(m_g - m_o) <= 0.01 * m_o + 1e-4), (m_g, m_o)
+    scene.close()
