@@ -31,7 +31,7 @@ namespace rtb {
 #define PS_LEAVE 8         // lanes that must have finished before the warp leaves the traversal loop to swap paths
 #define PS_WORK 28         // lanes with shading / regeneration work pending that trigger a shade phase ...
 #define PS_STALL 14        // ... or lanes that cannot traverse at all (both of their paths wait for the shade phase)
-#define PS_MIN_BLOCKS 5    // resident blocks per SM the kernel is compiled for: 96 registers, no spills (6/7/8 blocks spill and measured 4/6/11 % slower)
+#define PS_MIN_BLOCKS 6    // resident blocks per SM the kernel is compiled for: 80 registers with 32 B of spills; measured on C4: 5 blocks (94 registers, no spills) -4 %, 7 blocks (72 registers, 132 B of spills, 96 KB of L1) -6 %
 #ifndef PS_SPECULATE
 #define PS_SPECULATE 0  // speculative descent (postponed leaves): evaluated, 1-6 % slower on C4 with one-primitive leaves
 #endif
