@@ -34,7 +34,7 @@ WORLD, SEED, WIDTH, HEIGHT, ASPECT, MAX_DEPTH, JOB_SPP = "final_scene", 42, 800,
 # + 40*medium + shade terms; bytes = 32 B per node / primitive record touched.
 # DRAM bytes per camera path of the dominant kernel, from the committed ncu --set full captures (profiles/): C4 at 64 spp,
 # dram__bytes_read.sum + dram__bytes_write.sum of one launch divided by the paths of that launch
-NCU_DRAM_BYTES_PER_PATH = {"persistent": 10.78e6 / 40.96e6, "megakernel": 10.56e6 / 40.96e6, "wavefront": 597e6 / 504e3}
+NCU_DRAM_BYTES_PER_PATH = {"persistent": 18.72e6 / 40.96e6, "megakernel": 10.56e6 / 40.96e6, "wavefront": 597e6 / 504e3}
 
 ALGO = {"rays_per_path": 4.159, "aabb": 66.59, "sphere": 42.99, "rect": 60.77, "xform": 8.318, "medium": 8.318,
         "lambertian": 0.878, "metal": 0.0312, "dielectric": 0.315, "isotropic": 1.963, "perlin": 0.0682, "image": 0.0695,
