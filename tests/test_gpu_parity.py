@@ -236,3 +236,32 @@ def test_no_bias_at_high_sample_count(name, aspect, kw):
     m_g, m_o = accum.reshape(-1, 3).mean(axis=0) / spp, 0.5 * (a1 + a2).reshape(-1, 3).mean(axis=0) / spp
     assert np.all(np.abs(m_g - m_o) <= 0.01 * m_o + 1e-4), (m_g, m_o)
     scene.close()
+
+
+ALL_WORLDS = [("simple", 16 / 9), ("random", 1.5), ("random_chk", 1.5), ("two_spheres", 16 / 9), ("simple_light", 16 / 9), ("cornell_box", 1.0),
+              ("cornell_smoke", 1.0), ("earth", 16 / 9), ("debug_perlin", 1.0), ("final_scene", 1.0)]
+
+
+@pytest.mark.parametrize("name,aspect", ALL_WORLDS)
+def test_every_world_image_rmse_within_noise_floor(name, aspect):
+    """all ten worlds of the registry (worlds.rs:471-484) through the default pipeline: negative-radius glass, checker on
+    world-space p, Perlin on large spheres, rect and sphere emitters, rotated boxes as surfaces, the earth texture"""
+    world = rt.World(name)
+    scene = rt.Scene(world.build(42))
+    ow = S.OracleWorld(name, 42)
+    cam = S.make_camera(ow.lookfrom, ow.lookat, ow.vfov, aspect)
+    W, spp = 80, 96
+    H = int(W / aspect)
+    r = rt.Renderer.new_with_rng(cam, scene, world.background(), rt.RenderingParams(spp, H, W), rt.RecursiveRayTracer(50), rt.SeedableRngator(7))
+    _, accum = r.render_arrays()
+    assert r.stats["pipeline"] == abi.RT_PIPELINE_PERSISTENT  # what AUTO resolves to
+    a1, _, c1, _ = ow.render(cam.c, W, H, spp, render_seed=11)
+    a2, _, _, _ = ow.render(cam.c, W, H, spp, render_seed=12)
+    disp = lambda a: np.sqrt(np.clip(a / spp, 0.0, 1.0))
+    rm = lambda x, y: float(np.sqrt(np.mean((x - y) ** 2)))
+    floor = rm(disp(a1), disp(a2))
+    g = disp(accum.astype(np.float64))
+    got = 0.5 * (rm(g, disp(a1)) + rm(g, disp(a2)))
+    assert got <= 1.1 * floor + 1e-4, f"{name}: RMSE {got:.5f} vs noise floor {floor:.5f}"
+    assert abs(r.stats["rays"] / r.stats["paths"] - c1[1] / c1[0]) < 0.05 * c1[1] / c1[0]
+    scene.close()
