@@ -76,6 +76,7 @@ std::vector<CommSet> g_comm_sets;
 
 int get_comms(const std::vector<int>& devices, std::vector<ncclComm_t>& out) {
     std::lock_guard<std::mutex> lock(g_comm_mutex);
+    rtb::DeviceGuard restore(devices[0]);  // the caller's current device comes back on every exit
     for (auto& cs : g_comm_sets)
         if (cs.devices == devices) {
             out = cs.comms;
@@ -118,6 +119,9 @@ int get_comms(const std::vector<int>& devices, std::vector<ncclComm_t>& out) {
 extern "C" {
 
 void rt_sample_slice(int32_t sample_begin, int32_t sample_count, int32_t n_parts, int32_t part, int32_t* begin, int32_t* count) {
+    if (n_parts < 1) n_parts = 1;
+    if (part < 0) part = 0;
+    if (part >= n_parts) part = n_parts - 1;
     int32_t base = sample_count / n_parts, extra = sample_count % n_parts;
     if (count) *count = base + (part < extra ? 1 : 0);
     if (begin) *begin = sample_begin + part * base + std::min(part, extra);
@@ -140,6 +144,7 @@ int rt_render_multi(RtScene* const* scenes, int32_t n_scenes, const RtCamera* ca
     int begin = params->sample_begin;
     int count = params->sample_count > 0 ? params->sample_count : params->samples_per_pixel - begin;
     if (count <= 0) return rtb::set_error(RT_ERR_INVALID, "render: empty sample range");
+    rtb::DeviceGuard caller(devices[0]);  // whatever device the calling thread had current comes back on every exit
     std::vector<ncclComm_t> comms;
     int rc = get_comms(devices, comms);
     if (rc != RT_OK) return rc;
@@ -159,7 +164,15 @@ int rt_render_multi(RtScene* const* scenes, int32_t n_scenes, const RtCamera* ca
         }
     }
     RtScene* root = scenes[0];
-    cudaEvent_t t0 = nullptr, t1 = nullptr;
+    struct Events {  // destroyed on every exit
+        cudaEvent_t t0 = nullptr, t1 = nullptr;
+        ~Events() {
+            if (t0) cudaEventDestroy(t0);
+            if (t1) cudaEventDestroy(t1);
+        }
+    } ev;
+    cudaEvent_t& t0 = ev.t0;
+    cudaEvent_t& t1 = ev.t1;
     {
         rtb::DeviceGuard guard(root->device);
         CU_TRY(cudaEventCreate(&t0));
@@ -191,10 +204,7 @@ int rt_render_multi(RtScene* const* scenes, int32_t n_scenes, const RtCamera* ca
     }
     for (auto& t : threads) t.join();
     for (int g = 0; g < n_scenes; ++g)
-        if (codes[g] != RT_OK) {
-            cudaEventDestroy(t0), cudaEventDestroy(t1);
-            return rtb::set_error(codes[g], "device %d: %s", devices[g], messages[g].c_str());
-        }
+        if (codes[g] != RT_OK) return rtb::set_error(codes[g], "device %d: %s", devices[g], messages[g].c_str());
     if (cb) cb(count, count, user);
     // the one exchange step of the path: sum the accumulation buffers onto the root
     Nccl& n = nccl();
@@ -205,10 +215,7 @@ int rt_render_multi(RtScene* const* scenes, int32_t n_scenes, const RtCamera* ca
     }
     ncclResult_t r2 = n.GroupEnd();
     if (r == 0) r = r2;
-    if (r != 0) {
-        cudaEventDestroy(t0), cudaEventDestroy(t1);
-        return rtb::set_error(RT_ERR_CUDA, "ncclReduce failed: %s", n.GetErrorString(r));
-    }
+    if (r != 0) return rtb::set_error(RT_ERR_CUDA, "ncclReduce failed: %s", n.GetErrorString(r));
     for (int g = 1; g < n_scenes; ++g) {
         cudaSetDevice(devices[g]);
         CU_TRY(cudaStreamSynchronize(0));
@@ -229,7 +236,6 @@ int rt_render_multi(RtScene* const* scenes, int32_t n_scenes, const RtCamera* ca
         stats->device_ms = ms;  // root-device events around render + reduce + tonemap (every other device finishes before the reduce does)
         stats->pipeline_used = part[0].pipeline_used;
     }
-    cudaEventDestroy(t0), cudaEventDestroy(t1);
     return RT_OK;
 }
 

@@ -4,8 +4,8 @@
 // It replaces Renderer::render / render_pixel / trace_internal (src/raytrace.rs:172-198, :79-101).  Every lane owns TWO
 // camera paths, both as records in shared memory; registers hold the context of the one being traversed (ray, closest
 // hit so far, cursor), the other waits to be shaded or holds a fresh ray.  The warp alternates between
-//   extend  : while-while BVH traversal of the register paths (32-byte nodes, 128-bit __ldg, short stack); lanes vote
-//             between the inner-node loop and a leaf step, exactly like wf_extend_kernel;
+//   extend  : while-while BVH traversal of the paths in flight (32-byte nodes, 128-bit __ldg, short stack of
+//             (node, entry distance) pairs); lanes vote between the inner-node loop and a leaf step, as in wf_extend_kernel;
 //   shade   : when enough lanes hold a finished traversal (or an empty slot), those paths are shaded together —
 //             scatter / emit / background, terminated paths deposit beta * radiance with float REDs and are
 //             regenerated in place from a global camera-path counter (reserved in chunks, one atomic per 256 paths),
@@ -28,10 +28,12 @@ namespace rtb {
 #define PS_THREADS 128
 #define PS_DONE RTB_TRAVERSAL_DONE
 #define PS_MIN_DESCEND 6   // lanes that must still be descending inner nodes for the inner loop to keep going
-#define PS_LEAVE 8         // lanes that must have finished before the warp leaves the traversal loop to swap paths
+#define PS_LEAVE 8         // lanes that must have finished before the warp leaves the traversal loop (to start them on their other path)
 #define PS_WORK 28         // lanes with shading / regeneration work pending that trigger a shade phase ...
 #define PS_STALL 14        // ... or lanes that cannot traverse at all (both of their paths wait for the shade phase)
-#define PS_MIN_BLOCKS 6    // resident blocks per SM the kernel is compiled for: 80 registers with 32 B of spills; measured on C4: 5 blocks (94 registers, no spills) -4 %, 7 blocks (72 registers, 132 B of spills, 96 KB of L1) -6 %
+// resident blocks per SM the kernel is compiled for: 6 = 80 registers with 32 B of spills.  Measured on C4:
+// 5 blocks (94 registers, no spills) -4 %, 7 blocks (72 registers, 132 B of spills, only 96 KB of L1 left) -6 %
+#define PS_MIN_BLOCKS 6
 #ifndef PS_SPECULATE
 #define PS_SPECULATE 0  // speculative descent (postponed leaves): evaluated, 1-6 % slower on C4 with one-primitive leaves
 #endif
