@@ -140,3 +140,19 @@ def test_to_ppm_framing():  # main.rs:144,175-179
     lines = text.split("\n")
     assert lines[:3] == ["P3", "3 2", "255"]
     assert lines[3] == "9 10 11" and lines[6] == "0 1 2" and text.endswith("\n") and len(lines) == 3 + 6 + 1
+
+
+def test_header_is_plain_c_and_links_from_c(tmp_path):
+    """include/rt_b200.h compiled as C99 by gcc and a C client (tests/c_abi/abi_check.c) linked against librt_b200.so:
+    the hash it prints for a world equals the one obtained through ctypes"""
+    import subprocess
+    inc = os.path.join(S.ROOT, "include")
+    libdir = os.path.dirname(abi.LIB_PATH)
+    subprocess.check_call(["gcc", "-std=c99", "-pedantic", "-Wall", "-Werror", "-fsyntax-only", "-x", "c", os.path.join(inc, "rt_b200.h")])
+    exe = str(tmp_path / "abi_check")
+    subprocess.check_call(["gcc", "-std=c99", "-Wall", "-Werror", "-I", inc, os.path.join(S.ROOT, "tests", "c_abi", "abi_check.c"), "-o", exe,
+                           "-L", libdir, "-lrt_b200", "-Wl,-rpath," + libdir])
+    for world in ("cornell_smoke", "random"):
+        out = subprocess.run([exe, world], stdout=subprocess.PIPE, text=True, check=True).stdout.split()
+        d = rt.World(world).build(42)
+        assert out[0] == d.hash() and int(out[1]) == d.desc.n_nodes and int(out[2]) == d.n_draws
