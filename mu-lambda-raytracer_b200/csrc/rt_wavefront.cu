@@ -421,7 +421,9 @@ int launch_wavefront(RtScene* s, const DCamera& cam, const RtParams* p, int begi
     if (p->max_depth <= 0) return RT_OK;  // every path returns Color::ZERO at once (raytrace.rs:87-89)
     if (s->flat.prims.size() >= (1u << 24)) return set_error(RT_ERR_UNSUPPORTED, "wavefront pipeline: more than 2^24 primitives");
     unsigned long long total = (unsigned long long)p->width * p->height * (unsigned long long)count;
-    unsigned int n_slots = 1u << 21;  // 2 Mi paths in flight: per-round tails and launch gaps amortise (pool sweep)
+    // 4 Mi paths in flight (256 MB pool): measured on C4 with the final device code — 0.5 Mi 714, 1 Mi 961, 2 Mi 1087, 4 Mi 1173,
+    // 8 Mi 1106, 16 Mi 1056 Mpaths/s.  Per-round launch gaps and tails outweigh L2 residency of the pool.
+    unsigned int n_slots = 1u << 22;
     if (const char* e = getenv("RT_WF_SLOTS")) n_slots = std::max(1024u, (unsigned int)strtoul(e, nullptr, 10));
     int rc = ensure_state(s, n_slots);
     if (rc != RT_OK) return rc;
