@@ -45,7 +45,7 @@ def build(force=False, verbose=False):
     objs = []
     bdir = os.path.join(HERE, "build")
     os.makedirs(bdir, exist_ok=True)
-    for src in ("worlds.cpp", "scene_hash.cpp", "flatten.cpp"):
+    for src in ("worlds.cpp", "scene_hash.cpp", "flatten.cpp"):  # pure host code: g++
         s = os.path.join(CSRC, src)
         o = os.path.join(bdir, src + ".o")
         if force or _newer(o, [s] + headers):
@@ -53,7 +53,7 @@ def build(force=False, verbose=False):
             if verbose and out:
                 print(out)
         objs.append(o)
-    for src in ("rt_api.cu", "rt_wavefront.cu", "rt_warpfront.cu", "rt_persist.cu", "rt_multi.cu"):
+    for src in ("rt_api.cu", "rt_wavefront.cu", "rt_warpfront.cu", "rt_persist.cu", "rt_multi.cu", "dev_cache.cu"):
         cu = os.path.join(CSRC, src)
         cuo = os.path.join(bdir, src + ".o")
         if force or _newer(cuo, [cu] + headers):

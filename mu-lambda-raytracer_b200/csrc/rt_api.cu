@@ -87,12 +87,12 @@ __global__ void camera_kernel(DCamera cam, DRenderParams P, const int32_t* __res
 namespace {
 
 template <class T>
-int upload(const std::vector<T>& v, T** out, std::vector<void*>& owned, int64_t& bytes) {
+int upload(const std::vector<T>& v, T** out, std::vector<std::pair<void*, size_t>>& owned, int64_t& bytes) {
     *out = nullptr;
     size_t n = std::max<size_t>(v.size(), 1) * sizeof(T);  // never a null table
     void* p = nullptr;
-    CU_TRY(cudaMalloc(&p, n));
-    owned.push_back(p);
+    CU_TRY(rtb::cache_malloc(&p, n));
+    owned.emplace_back(p, n);
     if (!v.empty()) CU_TRY(cudaMemcpy(p, v.data(), v.size() * sizeof(T), cudaMemcpyHostToDevice));
     *out = (T*)p;
     bytes += (int64_t)n;
@@ -141,8 +141,9 @@ int upload_scene(RtScene* s) {
     for (auto& im : f.images) {
         cudaChannelFormatDesc cd = cudaCreateChannelDesc<uchar4>();
         cudaArray_t arr = nullptr;
-        CU_TRY(cudaMallocArray(&arr, &cd, im.width, im.height));
+        CU_TRY(rtb::cache_malloc_array(&arr, &cd, im.width, im.height));
         s->arrays.push_back(arr);
+        s->array_extent.emplace_back((size_t)im.width, (size_t)im.height);
         CU_TRY(cudaMemcpy2DToArray(arr, 0, 0, im.rgba.data(), (size_t)im.width * 4, (size_t)im.width * 4, im.height, cudaMemcpyHostToDevice));
         cudaResourceDesc rd{};
         rd.resType = cudaResourceTypeArray;
@@ -173,12 +174,13 @@ void free_scene(RtScene* s) {
     if (!s) return;
     {
         DeviceGuard g(s->device);
+        cudaDeviceSynchronize();  // cached blocks are handed to the next scene without a real free: nothing may still be using them
         for (auto t : s->textures) cudaDestroyTextureObject(t);
-        for (auto a : s->arrays) cudaFreeArray(a);
-        for (void* p : s->owned) cudaFree(p);
-        if (s->d_accum) cudaFree(s->d_accum);
-        if (s->d_rgb) cudaFree(s->d_rgb);
-        if (s->d_rays) cudaFree(s->d_rays);
+        for (size_t i = 0; i < s->arrays.size(); ++i) rtb::cache_free_array(s->arrays[i], s->array_extent[i].first, s->array_extent[i].second);
+        for (auto& b : s->owned) rtb::cache_free(b.first, b.second);
+        rtb::cache_free(s->d_accum, s->scratch_values * sizeof(float));
+        rtb::cache_free(s->d_rgb, s->scratch_values * sizeof(int32_t));
+        rtb::cache_free(s->d_rays, sizeof(unsigned long long));
         if (s->ev0) cudaEventDestroy(s->ev0);
         if (s->ev1) cudaEventDestroy(s->ev1);
         free_wavefront(s);
@@ -201,7 +203,7 @@ int create_scene(const RtSceneDesc* desc, int32_t root, bool build_bvh, int devi
     s->device = device;
     DeviceGuard g(device);
     rc = upload_scene(s);
-    if (rc == RT_OK && cudaMalloc(&s->d_rays, sizeof(unsigned long long)) != cudaSuccess) rc = set_error(RT_ERR_CUDA, "cudaMalloc failed");
+    if (rc == RT_OK && rtb::cache_malloc((void**)&s->d_rays, sizeof(unsigned long long)) != cudaSuccess) rc = set_error(RT_ERR_CUDA, "cudaMalloc failed");
     if (rc == RT_OK && (cudaEventCreate(&s->ev0) != cudaSuccess || cudaEventCreate(&s->ev1) != cudaSuccess)) rc = set_error(RT_ERR_CUDA, "cudaEventCreate failed");
     if (rc != RT_OK) {
         free_scene(s);
@@ -371,11 +373,11 @@ int rt_render(const RtScene* scene_, const RtCamera* cam, const RtParams* params
     DeviceGuard g(scene->device);
     size_t n_values = (size_t)3 * params->width * params->height;
     if (scene->scratch_values < n_values) {
-        if (scene->d_accum) cudaFree(scene->d_accum);
-        if (scene->d_rgb) cudaFree(scene->d_rgb);
+        rtb::cache_free(scene->d_accum, scene->scratch_values * sizeof(float));
+        rtb::cache_free(scene->d_rgb, scene->scratch_values * sizeof(int32_t));
         scene->d_accum = nullptr, scene->d_rgb = nullptr, scene->scratch_values = 0;
-        CU_TRY(cudaMalloc(&scene->d_accum, n_values * sizeof(float)));
-        CU_TRY(cudaMalloc(&scene->d_rgb, n_values * sizeof(int32_t)));
+        CU_TRY(rtb::cache_malloc((void**)&scene->d_accum, n_values * sizeof(float)));
+        CU_TRY(rtb::cache_malloc((void**)&scene->d_rgb, n_values * sizeof(int32_t)));
         scene->scratch_values = n_values;
     }
     int begin = params->sample_begin;

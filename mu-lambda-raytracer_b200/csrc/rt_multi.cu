@@ -155,11 +155,11 @@ int rt_render_multi(RtScene* const* scenes, int32_t n_scenes, const RtCamera* ca
         RtScene* s = scenes[g];
         rtb::DeviceGuard guard(s->device);
         if (s->scratch_values < n_values) {
-            if (s->d_accum) cudaFree(s->d_accum);
-            if (s->d_rgb) cudaFree(s->d_rgb);
+            rtb::cache_free(s->d_accum, s->scratch_values * sizeof(float));
+            rtb::cache_free(s->d_rgb, s->scratch_values * sizeof(int32_t));
             s->d_accum = nullptr, s->d_rgb = nullptr, s->scratch_values = 0;
-            CU_TRY(cudaMalloc(&s->d_accum, n_values * sizeof(float)));
-            CU_TRY(cudaMalloc(&s->d_rgb, n_values * sizeof(int32_t)));
+            CU_TRY(rtb::cache_malloc((void**)&s->d_accum, n_values * sizeof(float)));
+            CU_TRY(rtb::cache_malloc((void**)&s->d_rgb, n_values * sizeof(int32_t)));
             s->scratch_values = n_values;
         }
     }

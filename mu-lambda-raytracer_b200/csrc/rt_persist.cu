@@ -384,7 +384,7 @@ __global__ void __launch_bounds__(PS_THREADS, STATS ? 4 : PS_MIN_BLOCKS) persist
 // ---------------------------------------------------------------------------------------------------------------
 void free_persist(RtScene* s) {
     if (!s->ps) return;
-    if (s->ps->ctr) cudaFree(s->ps->ctr);
+    rtb::cache_free(s->ps->ctr, sizeof(PsCounters));
     delete s->ps;
     s->ps = nullptr;
 }
@@ -398,7 +398,7 @@ int launch_persist(RtScene* s, const DCamera& cam, const RtParams* p, int begin,
     if (!s->ps) {
         PersistState* w = new PersistState();
         s->ps = w;
-        CU_TRY(cudaMalloc(&w->ctr, sizeof(PsCounters)));
+        CU_TRY(rtb::cache_malloc((void**)&w->ctr, sizeof(PsCounters)));
         int per_sm = 0, sms = 0;
         CU_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, persist_kernel<false>, PS_THREADS, 0));
         if (const char* e = getenv("RT_PS_BLOCKS_PER_SM")) per_sm = std::min(per_sm, std::max(1, atoi(e)));

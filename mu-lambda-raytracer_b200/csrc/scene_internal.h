@@ -2,8 +2,10 @@
 #pragma once
 #include <cuda_runtime.h>
 
+#include <utility>
 #include <vector>
 
+#include "dev_cache.h"
 #include "flatten.h"
 #include "internal.h"
 #include "rt_types.h"
@@ -41,8 +43,9 @@ struct RtScene {
     int device = 0;
     rtb::DSceneView view{};
     rtb::FlatScene flat;  // host copy (info + hit -> description node mapping)
-    std::vector<void*> owned;
+    std::vector<std::pair<void*, size_t>> owned;  // (block, bytes): returned to the device cache on destruction
     std::vector<cudaArray_t> arrays;
+    std::vector<std::pair<size_t, size_t>> array_extent;
     std::vector<cudaTextureObject_t> textures;
     int64_t device_bytes = 0;
     rtb::OwnedDesc* desc = nullptr;  // deep copy of the description (sub-tree queries of rt_intersect_batch)

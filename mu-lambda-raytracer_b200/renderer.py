@@ -96,9 +96,12 @@ class SceneDescription:
         return bytes(out).hex()
 
     def __del__(self):
-        if getattr(self, "_owned", False) and self.ptr:
-            abi.load().rt_scene_desc_free(self.ptr)
-            self.ptr = None
+        try:
+            if getattr(self, "_owned", False) and self.ptr:
+                abi.load().rt_scene_desc_free(self.ptr)
+                self.ptr = None
+        except Exception:  # interpreter shutdown: the module globals may already be gone
+            pass
 
 
 class Scene:

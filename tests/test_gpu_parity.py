@@ -265,3 +265,29 @@ def test_every_world_image_rmse_within_noise_floor(name, aspect):
     assert got <= 1.1 * floor + 1e-4, f"{name}: RMSE {got:.5f} vs noise floor {floor:.5f}"
     assert abs(r.stats["rays"] / r.stats["paths"] - c1[1] / c1[0]) < 0.05 * c1[1] / c1[0]
     scene.close()
+
+
+def test_scene_recreation_reuses_cached_device_memory():
+    """create / render / destroy in a loop (what a frame-by-frame host such as movie.py does): the blocks of a destroyed
+    scene are handed to the next one (csrc/dev_cache.h), results stay identical, other scenes are not disturbed"""
+    world = rt.World("final_scene")
+    desc = world.build(42)
+    info = world.camera()
+    cam = S.make_camera(info["lookfrom"], info["lookat"], info["field_of_view"], 1.0)
+    other = rt.Scene(rt.World("cornell_smoke").build(0))
+    ref = None
+    for k in range(5):
+        scene = rt.Scene(desc)
+        r = rt.Renderer.new_with_rng(cam, scene, world.background(), rt.RenderingParams(8, 64, 64), rt.RecursiveRayTracer(50), rt.SeedableRngator(1))
+        _, accum = r.render_arrays()
+        rays = r.stats["rays"]
+        if ref is None:
+            ref = (accum.copy(), rays)
+        assert rays == ref[1] and np.allclose(accum, ref[0], rtol=1e-5, atol=1e-5)
+        scene.close()
+    oi = rt.World("cornell_smoke").camera()
+    ocam = S.make_camera(oi["lookfrom"], oi["lookat"], oi["field_of_view"], 1.0)
+    r = rt.Renderer.new_with_rng(ocam, other, rt.BlackBackground(), rt.RenderingParams(4, 32, 32), rt.RecursiveRayTracer(50), rt.SeedableRngator(1))
+    _, a = r.render_arrays()
+    assert np.isfinite(a).all() and a.sum() > 0
+    other.close()
