@@ -324,7 +324,7 @@ def main():
     ap.add_argument("--pipeline", default="auto", choices=["auto", "megakernel", "wavefront", "wavefront_smem", "persistent"])
     ap.add_argument("--samples-per-item", type=int, default=0)
     ap.add_argument("--e2e-steps", type=int, default=3)
-    ap.add_argument("--cpu-spp", type=int, default=64, help="spp of the bounded CPU-baseline sample (0 = skip)")
+    ap.add_argument("--cpu-spp", type=int, default=128, help="spp of the bounded CPU-baseline sample (0 = skip)")
     ap.add_argument("--ref-spp", type=int, default=32, help="spp per step of --impl reference")
     args = ap.parse_args()
     if args.impl == "reference":
