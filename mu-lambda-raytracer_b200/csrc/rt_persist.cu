@@ -418,8 +418,9 @@ int launch_persist(RtScene* s, const DCamera& cam, const RtParams* p, int begin,
     }
     PersistState* w = s->ps;
     const unsigned long long npix = (unsigned long long)p->width * p->height;
-    // bound one launch to ~2^29 camera paths so that progress can be reported
-    const int samples_per_launch = (int)std::max<unsigned long long>(1, (1ull << 29) / npix);
+    // one launch = up to 2^29 camera paths when progress is reported (a quarter of a second on C4), 2^33 otherwise: every
+    // launch ends with a tail in which the longest paths run on a mostly idle machine
+    const int samples_per_launch = (int)std::min<unsigned long long>(1u << 30, std::max<unsigned long long>(1, (1ull << (cb ? 29 : 33)) / npix));
     int done = 0;
     while (done < count) {
         int samples = std::min(count - done, samples_per_launch);
