@@ -30,7 +30,7 @@ import numpy as np  # noqa: E402
 WORLD, SEED, WIDTH, HEIGHT, ASPECT, MAX_DEPTH, JOB_SPP = "final_scene", 42, 800, 800, 1.0, 50, 10000
 
 # Algorithmic work of the REFERENCE's traversal per camera path on C4, counted by the oracle's instrumentation
-# (tools/algo_work.py: 800x800, 16 spp, seed 42).  flops = 27*aabb + 45*sphere + 15*rect + 12*xform
+# (tests/golden/algo_work.py: 800x800, 16 spp, seed 42).  flops = 27*aabb + 45*sphere + 15*rect + 12*xform
 # + 40*medium + shade terms; bytes = 32 B per node / primitive record touched.
 # DRAM bytes per camera path of the dominant kernel, from the committed ncu --set full captures (profiles/): C4 at 64 spp,
 # dram__bytes_read.sum + dram__bytes_write.sum of one launch divided by the paths of that launch
@@ -38,7 +38,7 @@ NCU_DRAM_BYTES_PER_PATH = {"persistent": 18.72e6 / 40.96e6, "megakernel": 10.56e
 
 ALGO = {"rays_per_path": 4.159, "aabb": 66.59, "sphere": 42.99, "rect": 60.77, "xform": 8.318, "medium": 8.318,
         "lambertian": 0.878, "metal": 0.0312, "dielectric": 0.315, "isotropic": 1.963, "perlin": 0.0682, "image": 0.0695,
-        "background": 0.886}  # tools/algo_work.py 16 (frozen in BASELINE.md section 4)
+        "background": 0.886}  # tests/golden/algo_work.py 16 (frozen in BASELINE.md section 4)
 
 
 def algo_flops_per_path():

@@ -1,12 +1,12 @@
 #!/usr/bin/env python
 """Algorithmic work of the REFERENCE's traversal per camera path, counted by the oracle's instrumentation
 on the reference's own BVH topology: the frozen figures behind bench.py's roofline and BASELINE.md §4.
-usage: python tools/algo_work.py [spp]   (full-resolution frames at reduced spp; cost is linear in spp)"""
+usage: python tests/golden/algo_work.py [spp]   (full-resolution frames at reduced spp; cost is linear in spp)"""
 import json
 import os
 import sys
 
-ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+ROOT = os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 sys.path.insert(0, ROOT)
 sys.path.insert(0, os.path.join(ROOT, "tests"))
 import support as S  # noqa: E402
