@@ -204,7 +204,8 @@ int rt_scene_info(const RtScene* scene, int32_t* n_prims, int32_t* n_bvh_nodes, 
  *   accum_rgb: optional, 3*W*H floats, sum of sample radiance (not divided by spp)
  *   rgb:       optional, 3*W*H int32 in 0..=255 after to_rgb (raytrace.rs:59-68);
  *              row j = 0 is the BOTTOM row, exactly like the reference's Vec<Vec<RGB>>.
- * Blocking; cb is invoked on the calling host thread only.
+ * Blocking; cb is invoked on the calling host thread only.  Thread-compatible: different scenes may render from
+ * different host threads at the same time, one scene serves one render call at a time (it owns scratch buffers).
  */
 int rt_render(const RtScene* scene, const RtCamera* cam, const RtParams* params, float* accum_rgb,
               int32_t* rgb, RtProgressFn cb, void* user, RtStats* stats);
