@@ -26,10 +26,14 @@ def furnace_desc():
     iso = b.material(abi.RT_MAT_ISOTROPIC, tex=white)
     items = [b.sphere((0.0, -100.5, -1.0), 100.0, lam_chk), b.sphere((0.0, 0.0, -1.0), 0.5, lam), b.sphere((1.1, 0.0, -1.0), 0.5, glass),
              b.sphere((1.1, 0.0, -1.0), -0.4, glass), b.translate((-1.6, -0.5, -1.4), b.rotate(1, 25.0, b.block((0.0, 0.0, 0.0), (0.7, 0.9, 0.7), lam)))]
-    fog_boundary = b.sphere((-0.2, 0.3, -0.2), 0.45, glass)
-    fog = b.medium(fog_boundary, 3.0, (1.0, 1.0, 1.0))
-    b.materials[b.nodes[fog].material] = b.materials[iso]  # the medium's phase material: white isotropic
-    root = b.group(abi.RT_NODE_LIST, [b.group(abi.RT_NODE_BVH, items), fog])
+    fogs = []
+    # three media (overlapping each other and the surfaces): a dense ball, a thin global haze, a rotated box of smoke
+    for boundary, density in ((b.sphere((-0.2, 0.3, -0.2), 0.45, glass), 3.0), (b.sphere((0.0, 0.0, 0.0), 50.0, glass), 0.02),
+                              (b.translate((0.4, -0.4, 0.2), b.rotate(1, -18.0, b.block((0.0, 0.0, 0.0), (0.6, 0.6, 0.6), lam))), 1.5)):
+        fog = b.medium(boundary, density, (1.0, 1.0, 1.0))
+        b.materials[b.nodes[fog].material] = b.materials[iso]  # the medium's phase material: white isotropic
+        fogs.append(fog)
+    root = b.group(abi.RT_NODE_LIST, [b.group(abi.RT_NODE_BVH, items)] + fogs)
     desc = b.finish(root, background=abi.RT_BG_GRADIENT)
     for i in range(3):
         desc.contents.background_top[i] = 1.0
