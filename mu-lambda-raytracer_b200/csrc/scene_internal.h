@@ -55,9 +55,9 @@ struct RtScene {
     size_t scratch_values = 0;
     unsigned long long* d_rays = nullptr;
     cudaEvent_t ev0 = nullptr, ev1 = nullptr;
-    rtb::WavefrontState* wf = nullptr;  // global path pool + queues (RT_PIPELINE_WAVEFRONT_GLOBAL), allocated on first use
+    rtb::WavefrontState* wf = nullptr;  // global path pool + queues (RT_PIPELINE_WAVEFRONT), allocated on first use
     rtb::PersistState* ps = nullptr;    // counters of the persistent pipeline (RT_PIPELINE_PERSISTENT)
-    rtb::WarpfrontState* wa = nullptr;  // launch state of the shared-memory wavefront (RT_PIPELINE_WAVEFRONT)
+    rtb::WarpfrontState* wa = nullptr;  // launch state of the shared-memory wavefront (RT_PIPELINE_WAVEFRONT_SMEM)
 };
 
 namespace rtb {
