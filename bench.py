@@ -29,6 +29,15 @@ import numpy as np  # noqa: E402
 
 WORLD, SEED, WIDTH, HEIGHT, ASPECT, MAX_DEPTH, JOB_SPP = "final_scene", 42, 800, 800, 1.0, 50, 10000
 
+
+def baseline_metric():
+    """the headline metric exactly as BASELINE.json words it (unit: Mpaths/s = million camera paths per second)"""
+    try:
+        with open(os.path.join(ROOT, "BASELINE.json")) as f:
+            return json.load(f)["metric"]
+    except Exception:
+        return "Mpaths/s on final_scene 800x800 (device-timed) vs host-CPU reference"
+
 # Algorithmic work of the REFERENCE's traversal per camera path on C4, counted by the oracle's instrumentation
 # (tests/golden/algo_work.py: 800x800, 16 spp, seed 42; DESIGN.md section 3).  flops = 27*aabb + 45*sphere + 15*rect + 12*xform
 # + 40*medium + shade terms (SURVEY §8d); bytes = 32 B per node / primitive record touched.
@@ -121,7 +130,7 @@ def run_reference(args):
     value, ms, cores, rpp = cpu_reference_run(spp, args.steps, args.warmup)
     sample = f"full 800x800 frame at {spp} spp per step ({WIDTH * HEIGHT * spp} camera paths; the C4 job is {JOB_SPP} spp), max_depth {MAX_DEPTH}"
     line = {
-        "impl": "reference", "metric": "Mpaths/s", "value": value, "unit": "Mpaths/s", "n_gpus": args.gpus, "steps": args.steps,
+        "impl": "reference", "metric": baseline_metric(), "value": value, "unit": "Mpaths/s", "n_gpus": args.gpus, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64",
         "data": "synthetic",
         "config": {"workload": f"C4 {WORLD} {WIDTH}x{HEIGHT} seed {SEED} max_depth {MAX_DEPTH}", "spp_per_step": spp,
@@ -285,7 +294,7 @@ def run_b200(args):
         achieved = flops / (render_ms / 1e3) / 1e12
         accum_bytes = 3 * 4 * WIDTH * HEIGHT * spp  # one float RED per channel per terminated path (upper bound)
         line = {
-            "metric": "Mpaths/s", "value": value, "unit": "Mpaths/s", "n_gpus": world_size, "steps": args.steps, "warmup": args.warmup,
+            "metric": baseline_metric(), "value": value, "unit": "Mpaths/s", "n_gpus": world_size, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": ms_total / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
             "data": "synthetic",
             "config": {"workload": f"C4 {WORLD} {WIDTH}x{HEIGHT} seed {SEED} max_depth {MAX_DEPTH}", "spp_per_step_per_gpu": spp,
