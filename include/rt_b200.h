@@ -160,7 +160,7 @@ typedef struct RtParams {
     int32_t pipeline;          /* RT_PIPELINE_* */
     int32_t device;            /* ignored: a scene lives on the device it was created on */
     int32_t samples_per_item;  /* tuning: consecutive samples one GPU thread integrates (0 = auto) */
-    int32_t reserved;
+    int32_t bvh_layout;        /* persistent pipeline: 0 = auto, 2 = binary 32-byte-node BVH, 4 = 4-wide 128-byte-node BVH */
 } RtParams;
 
 typedef struct RtScene RtScene; /* opaque: flattened scene resident on one device */
@@ -240,6 +240,7 @@ void rt_sample_slice(int32_t sample_begin, int32_t sample_count, int32_t n_parts
  *         closest hit of that subtree is returned (root = whole world, media excluded
  *         unless node is itself a MEDIUM, in which case `t` = entry and `u` = exit of
  *         the clipped boundary interval and no free-flight sampling is done).
+ *         node = -1: the whole world through the binary BVH; node = -2: through the 4-wide BVH.
  *   rays: N x 8 floats: origin xyz, direction xyz (NOT normalised), t_min, t_max.
  */
 int rt_intersect_batch(const RtScene* scene, int32_t node, const float* rays, int64_t n, RtHit* out);

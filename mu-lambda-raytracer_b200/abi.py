@@ -63,7 +63,7 @@ class RtParams(C.Structure):
     _fields_ = [("width", C.c_int32), ("height", C.c_int32), ("samples_per_pixel", C.c_int32),
                 ("max_depth", C.c_int32), ("seed", C.c_uint64), ("sample_begin", C.c_int32),
                 ("sample_count", C.c_int32), ("pipeline", C.c_int32), ("device", C.c_int32),
-                ("samples_per_item", C.c_int32), ("reserved", C.c_int32)]
+                ("samples_per_item", C.c_int32), ("bvh_layout", C.c_int32)]
 
 
 class RtHit(C.Structure):

@@ -300,6 +300,7 @@ class Flattener {
 
     // ---- SAH BVH over prim_box ----
     std::vector<int> order;
+    static const int kMedianDepth = 20;
     int kMaxLeaf = 1;  // one primitive per leaf measured fastest (C2 +1 %, C3 +5 %, C4 +2 % over 4); RT_BVH_MAX_LEAF overrides
 
     Box3 bounds_of(int begin, int end) const {
@@ -338,10 +339,25 @@ class Flattener {
             }
         }
         bool leaf = n <= kMaxLeaf && (n < 2 || (double)n <= best_cost);
-        if (depth >= RTB_BVH_STACK - 2 && n <= 255) leaf = true;  // never outgrow the traversal stack
         if (leaf) {
-            out.nodes[idx].a = ~(begin | (n << 24)), out.nodes[idx].b = n;  // ready-made traversal link
+            out.nodes[idx].a = ~(begin | (n << 24)), out.nodes[idx].b = n;  // ready-made traversal link (n <= kMaxLeaf <= 8)
             return;
+        }
+        if (depth >= kMedianDepth || best_axis < 0) {
+            // A skewed SAH tree (nested or concentric primitives) could outgrow the traversal stack.  From this depth on
+            // the subtree is split at the median of the widest centroid axis: at most ceil(log2 n) <= 24 further levels,
+            // so the whole tree stays below RTB_BVH_STACK (checked after the build).
+            Box3 cb;
+            cb.reset();
+            for (int i = begin; i < end; ++i) {
+                const Box3& pb = prim_box[order[i]];
+                double c[3] = {pb.lo[0] + pb.hi[0], pb.lo[1] + pb.hi[1], pb.lo[2] + pb.hi[2]};
+                cb.grow(c);
+            }
+            best_axis = 0;
+            for (int a = 1; a < 3; ++a)
+                if (cb.hi[a] - cb.lo[a] > cb.hi[best_axis] - cb.lo[best_axis]) best_axis = a;
+            best_split = n / 2;
         }
         std::stable_sort(order.begin() + begin, order.begin() + end, [&](int x, int y) {
             return prim_box[x].lo[best_axis] + prim_box[x].hi[best_axis] < prim_box[y].lo[best_axis] + prim_box[y].hi[best_axis];
@@ -369,6 +385,107 @@ class Flattener {
         std::vector<int32_t> n2(n);
         for (int i = 0; i < n; ++i) p2[i] = out.prims[order[i]], n2[i] = out.prim_node[order[i]];
         out.prims.swap(p2), out.prim_node.swap(n2);
+        if (out.bvh_depth > RTB_BVH_STACK - 2) {
+            fail(RT_ERR_UNSUPPORTED, "BVH deeper than the traversal stack");
+            return;
+        }
+        collapse4();
+    }
+
+    // ---- 4-wide collapse of the binary tree (DNode4, rt_types.h).  Which binary nodes survive as wide nodes is chosen
+    // by the dynamic programme of Ylitie, Karras & Laine (HPG 2017, section 4.1) for K = 4: cost[n][j] = the smallest
+    // summed surface area of wide nodes with which subtree n can fill at most j child slots of its parent.  Leaves hold
+    // exactly one primitive, so their cost is the same in every arrangement and drops out.  Only for scenes whose
+    // links fit 16 bits; otherwise nodes4 stays empty and every pipeline walks the binary tree.
+    static double area_of(const DNode& n) {
+        double d[3] = {(double)n.hi[0] - n.lo[0], (double)n.hi[1] - n.lo[1], (double)n.hi[2] - n.lo[2]};
+        return d[0] * d[1] + d[1] * d[2] + d[2] * d[0];
+    }
+    struct Cost4 {
+        double c[4];  // c[j], j = 1..3 (c[0] unused)
+    };
+    std::vector<Cost4> cost4;
+    bool wide_overflow = false;
+    double distribute4(int n2, int j) const {  // best split of j slots between the two children of binary node n2
+        int l = out.nodes[n2].a, r = l + 1;
+        double best = std::numeric_limits<double>::infinity();
+        for (int k = 1; k < j; ++k) best = std::min(best, cost4[l].c[k] + cost4[r].c[j - k]);
+        return best;
+    }
+    void solve4(int n2) {
+        Cost4& me = cost4[n2];
+        if (out.nodes[n2].a < 0) {
+            me.c[1] = me.c[2] = me.c[3] = 0.0;
+            return;
+        }
+        solve4(out.nodes[n2].a), solve4(out.nodes[n2].a + 1);
+        me.c[1] = area_of(out.nodes[n2]) + distribute4(n2, 4);
+        me.c[2] = std::min(me.c[1], distribute4(n2, 2));
+        me.c[3] = std::min(me.c[2], distribute4(n2, 3));
+    }
+    void expand4(int n2, int j, std::vector<int>& kids) const {  // the binary nodes that fill <= j slots at cost4[n2].c[j]
+        if (out.nodes[n2].a < 0 || j == 1) {
+            kids.push_back(n2);
+            return;
+        }
+        if (cost4[n2].c[j] == cost4[n2].c[j - 1]) return expand4(n2, j - 1, kids);
+        int l = out.nodes[n2].a, r = l + 1;
+        for (int k = 1; k < j; ++k)
+            if (cost4[l].c[k] + cost4[r].c[j - k] == cost4[n2].c[j]) {
+                expand4(l, k, kids), expand4(r, j - k, kids);
+                return;
+            }
+        kids.push_back(n2);  // not reached (the minimum above is attained by some k)
+    }
+    int make4(int n2, int depth) {
+        int me = (int)out.nodes4.size();
+        out.nodes4.push_back(DNode4{});
+        out.bvh4_depth = std::max(out.bvh4_depth, depth);
+        if (me >= RTB_WIDE_MAX_NODES) wide_overflow = true;
+        if (wide_overflow) return 0;
+        std::vector<int> kids;
+        if (out.nodes[n2].a < 0) {
+            kids.push_back(n2);  // the whole world is one leaf
+        } else {
+            int l = out.nodes[n2].a, r = l + 1;
+            double want = cost4[n2].c[1] - area_of(out.nodes[n2]);
+            for (int k = 1; k < 4; ++k)
+                if (cost4[l].c[k] + cost4[r].c[4 - k] == want) {
+                    expand4(l, k, kids), expand4(r, 4 - k, kids);
+                    break;
+                }
+            if (kids.empty()) kids.push_back(l), kids.push_back(r);
+        }
+        for (int c = 0; c < 4; ++c) {
+            uint32_t link = RTB_LINK4_EMPTY;
+            float box[6] = {0, 0, 0, 0, 0, 0};
+            if (c < (int)kids.size()) {
+                const DNode k = out.nodes[kids[c]];
+                for (int a = 0; a < 3; ++a) box[a] = k.lo[a], box[3 + a] = k.hi[a];
+                if (k.a < 0) {
+                    int v = ~k.a;
+                    link = RTB_LINK4_LEAF | (uint32_t)(v & 0xFFFFFF);  // exactly one primitive per leaf here
+                } else {
+                    link = (uint32_t)make4(kids[c], depth + 1);
+                }
+            }
+            DNode4& dst = out.nodes4[me];  // looked up after the recursion, which reallocates out.nodes4
+            dst.xy[c][0] = box[0], dst.xy[c][1] = box[1], dst.xy[c][2] = box[3], dst.xy[c][3] = box[4];
+            dst.loz[c] = box[2], dst.hiz[c] = box[5];
+            dst.link[c] = link;
+        }
+        return me;
+    }
+    void collapse4() {
+        out.nodes4.clear();
+        out.bvh4_depth = 0;
+        int n = (int)out.prims.size();
+        if (n == 0 || n > RTB_WIDE_MAX_PRIMS || kMaxLeaf != 1 || getenv("RT_BVH_NO_WIDE")) return;
+        cost4.assign(out.nodes.size(), Cost4{});
+        solve4(0);
+        make4(0, 1);
+        // a step pushes at most three entries, so 3 x depth bounds the stack
+        if (wide_overflow || 3 * out.bvh4_depth > RTB_WIDE_STACK) out.nodes4.clear(), out.bvh4_depth = 0;
     }
 
     bool tables() {

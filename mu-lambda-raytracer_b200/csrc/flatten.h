@@ -10,6 +10,7 @@ namespace rtb {
 
 struct FlatScene {
     std::vector<DNode> nodes;       // BVH over the surface primitives, root = 0
+    std::vector<DNode4> nodes4;     // the same tree collapsed 4-wide (empty when it does not fit 16-bit links or leaves hold > 1 primitive)
     std::vector<DPrim> prims;       // in BVH leaf order
     std::vector<int32_t> prim_node; // description node of each primitive
     std::vector<DBigSphere> big;
@@ -27,6 +28,7 @@ struct FlatScene {
     int32_t bg_kind = 0;
     float bg_top[3] = {0, 0, 0}, bg_bottom[3] = {0, 0, 0};
     int32_t bvh_depth = 0;
+    int32_t bvh4_depth = 0;
 };
 
 // Flatten the subtree rooted at `root` (normally desc->root).  With build_bvh = false the primitives are

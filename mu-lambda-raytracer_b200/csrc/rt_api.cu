@@ -118,6 +118,7 @@ int upload_scene(RtScene* s) {
     FlatScene& f = s->flat;
     DSceneView& v = s->view;
     DNode* nodes;
+    DNode4* nodes4;
     DPrim* prims;
     DBigSphere* big;
     DInstance* inst;
@@ -128,6 +129,7 @@ int upload_scene(RtScene* s) {
     unsigned short* pperm;
     int rc;
     if ((rc = upload(f.nodes, &nodes, s->owned, s->device_bytes))) return rc;
+    if ((rc = upload(f.nodes4, &nodes4, s->owned, s->device_bytes))) return rc;
     if ((rc = upload(f.prims, &prims, s->owned, s->device_bytes))) return rc;
     if ((rc = upload(f.big, &big, s->owned, s->device_bytes))) return rc;
     if ((rc = upload(f.inst, &inst, s->owned, s->device_bytes))) return rc;
@@ -161,7 +163,7 @@ int upload_scene(RtScene* s) {
     }
     DImage* dimages;
     if ((rc = upload(images, &dimages, s->owned, s->device_bytes))) return rc;
-    v.nodes = nodes, v.prims = prims, v.big = big, v.inst = inst, v.mats = mats, v.texs = texs, v.media = media;
+    v.nodes = nodes, v.nodes4 = f.nodes4.empty() ? nullptr : nodes4, v.n_nodes4 = (int)f.nodes4.size(), v.prims = prims, v.big = big, v.inst = inst, v.mats = mats, v.texs = texs, v.media = media;
     v.perlin_vec = pvec, v.perlin_perm = pperm, v.images = dimages;
     v.n_nodes = (int)f.nodes.size(), v.n_prims = (int)f.prims.size(), v.n_media = (int)f.media.size();
     v.n_perlin = (int)(f.perlin_vec.size() / (4 * RTB_PERLIN_POINTS));
@@ -420,8 +422,7 @@ int rt_intersect_batch(const RtScene* scene, int32_t node, const float* rays, in
     DeviceGuard g(scene->device);
     const RtScene* target = scene;
     RtScene* sub = nullptr;
-    int mode = QUERY_BVH;
-    std::vector<int32_t> node_of_prim;
+    int mode = node == -2 ? QUERY_BVH4 : QUERY_BVH;  // -2: the whole world through the 4-wide tree (binary tree if the scene has none)
     if (node >= 0 && scene->desc && node != scene->desc->d.root) {
         // a sub-tree: flatten it on its own (no outer transforms) and test it by brute force
         if (node >= scene->desc->d.n_nodes) return set_error(RT_ERR_INVALID, "rt_intersect_batch: node %d out of range", node);

@@ -31,6 +31,17 @@
 #define RTB_DEV_NOINLINE static __device__ __noinline__
 namespace rtb {
 RTB_DEV float4 ld4(const void* p) { return __ldg(reinterpret_cast<const float4*>(p)); }
+// one 256-bit load (sm_100: LDG.E.256) of a 32-byte-aligned record: half the load instructions and L1 requests of 2 x 128 bit
+struct F8 {
+    float4 lo, hi;
+};
+RTB_DEV F8 ld8(const void* p) {
+    F8 v;
+    asm("ld.global.nc.v8.f32 {%0, %1, %2, %3, %4, %5, %6, %7}, [%8];"
+        : "=f"(v.lo.x), "=f"(v.lo.y), "=f"(v.lo.z), "=f"(v.lo.w), "=f"(v.hi.x), "=f"(v.hi.y), "=f"(v.hi.z), "=f"(v.hi.w)
+        : "l"(p));
+    return v;
+}
 RTB_DEV uint32_t mulhi32(uint32_t a, uint32_t b) { return __umulhi(a, b); }
 RTB_DEV float u32_to_unit(uint32_t x) { return __uint2float_rz(x) * 2.3283064365386963e-10f; }
 RTB_DEV void sincos_2pi(float x, float* s, float* c) { sincospif(2.0f * x, s, c); }
@@ -54,6 +65,14 @@ struct float4 {
 inline float4 ld4(const void* p) {
     float4 v;
     memcpy(&v, p, 16);
+    return v;
+}
+struct F8 {
+    float4 lo, hi;
+};
+inline F8 ld8(const void* p) {
+    F8 v;
+    memcpy(&v, p, 32);
     return v;
 }
 inline uint32_t mulhi32(uint32_t a, uint32_t b) { return (uint32_t)(((uint64_t)a * b) >> 32); }
@@ -191,13 +210,17 @@ struct PrimRec {  // a DPrim in registers
     uint32_t meta;
     int32_t mat;
 };
-RTB_DEV PrimRec load_prim(const DPrim* p) {
-    float4 a = ld4(p), b = ld4(reinterpret_cast<const char*>(p) + 16);
+RTB_DEV PrimRec prim_from(const float4& a, const float4& b) {
     PrimRec r;
     r.v0 = a.x, r.v1 = a.y, r.v2 = a.z, r.v3 = a.w, r.v4 = b.x, r.v5 = b.y;
     r.meta = as_uint(b.z), r.mat = (int32_t)as_uint(b.w);
     return r;
 }
+RTB_DEV PrimRec load_prim(const DPrim* p) {  // an element of the 32-byte-aligned primitive array
+    const F8 v = ld8(p);
+    return prim_from(v.lo, v.hi);
+}
+RTB_DEV PrimRec load_prim16(const DPrim* p) { return prim_from(ld4(p), ld4(reinterpret_cast<const char*>(p) + 16)); }  // 16-byte aligned only
 RTB_DEV int prim_instance(const PrimRec& p) { return (int)((p.meta >> PRIM_INST_SHIFT) & PRIM_INST_MASK); }
 
 // Sphere::hit (shapes.rs:57-82).  `from_surface`: the ray starts on this very sphere, so one root is
@@ -414,7 +437,8 @@ RTB_DEV void closest_hit(const DSceneView& S, const Ray& r, float tmin, float tm
             cur = stack_pop(stack, sp, t_best, nr.pad);
         } else {
             const char* base = reinterpret_cast<const char*>(S.nodes + cur);
-            float4 l0 = ld4(base), l1 = ld4(base + 16), r0 = ld4(base + 32), r1 = ld4(base + 48);
+            const F8 ln = ld8(base), rn = ld8(base + 32);
+            const float4 l0 = ln.lo, l1 = ln.hi, r0 = rn.lo, r1 = rn.hi;
             float tl, tr;
             bool hl = slab_node(l0, l1, nr, tmin, t_best, tl);
             bool hr = slab_node(r0, r1, nr, tmin, t_best, tr);
@@ -430,6 +454,95 @@ RTB_DEV void closest_hit(const DSceneView& S, const Ray& r, float tmin, float tm
                 cur = lr;
             } else {
                 cur = stack_pop(stack, sp, t_best, nr.pad);
+            }
+        }
+    }
+}
+
+// ------------------------------------------------------------------ 4-wide BVH traversal (DNode4, rt_types.h)
+// One step fetches a 128-byte node (seven 128-bit loads) and tests its four child boxes with the same conservative
+// FMA-form slabs as slab_node.  Every child yields ONE 32-bit key: (bits(entry distance) & 0xFFFF0000) | 16-bit link,
+// or RTB_KEY_MISS.  Entry distances are >= t_min > 0, so keys order like distances (to bf16 resolution, rounded
+// down = conservative): a five-exchange network on the keys sorts the children, the nearest becomes the cursor and the
+// others are pushed farthest first — as 4-byte stack entries that still carry the distance for the pop-time cull.
+#define RTB_KEY_MISS 0xFFFFFFFFu
+RTB_DEV uint32_t child_key(const float4& xy, float loz, float hiz, uint32_t link, const NodeRay& q, float tmin, float tmax) {
+#if defined(__CUDA_ARCH__) && !defined(RTB_HOST_EMULATION) && RTB_USE_FFMA2
+    const float2 ixy = make_float2(q.inv.x, q.inv.y), nxy = make_float2(q.noi.x, q.noi.y);
+    const float2 a2 = __ffma2_rn(make_float2(xy.x, xy.y), ixy, nxy), b2 = __ffma2_rn(make_float2(xy.z, xy.w), ixy, nxy);
+    const float ax = a2.x, ay = a2.y, bx = b2.x, by = b2.y;
+#else
+    float ax = fmaf(xy.x, q.inv.x, q.noi.x), bx = fmaf(xy.z, q.inv.x, q.noi.x);
+    float ay = fmaf(xy.y, q.inv.y, q.noi.y), by = fmaf(xy.w, q.inv.y, q.noi.y);
+#endif
+    float az = fmaf(loz, q.inv.z, q.noi.z), bz = fmaf(hiz, q.inv.z, q.noi.z);
+    float tn = fmaxf(fmaxf(fminf(ax, bx), fminf(ay, by)), fmaxf(fminf(az, bz), tmin));
+    float tf = fminf(fminf(fmaxf(ax, bx), fmaxf(ay, by)), fminf(fmaxf(az, bz), tmax));
+    bool hit = tn <= fmaf(tf, 1.0000004f, q.pad);
+    return hit ? ((as_uint(tn) & 0xFFFF0000u) | link) : RTB_KEY_MISS;  // an empty slot's link is all ones: MISS either way
+}
+RTB_DEV void key_exchange(uint32_t& a, uint32_t& b) {
+    const uint32_t lo = a < b ? a : b, hi = a < b ? b : a;
+    a = lo, b = hi;
+}
+// a DNode4 in registers
+struct Node4Regs {
+    float4 c0, c1, c2, c3, lz, hz, lk;
+};
+RTB_DEV Node4Regs node4_fetch(const DNode4* nodes4, uint32_t node) {
+    const char* base = reinterpret_cast<const char*>(nodes4 + node);
+    const F8 a = ld8(base), b = ld8(base + 32), c = ld8(base + 64), d = ld8(base + 96);  // 128-byte aligned
+    Node4Regs n;
+    n.c0 = a.lo, n.c1 = a.hi, n.c2 = b.lo, n.c3 = b.hi, n.lz = c.lo, n.hz = c.hi, n.lk = d.lo;
+    return n;
+}
+// the four child keys of a node, ascending (misses last)
+RTB_DEV void node4_sorted_keys(const Node4Regs& n, const NodeRay& q, float tmin, float tmax, uint32_t& k0, uint32_t& k1, uint32_t& k2, uint32_t& k3) {
+    k0 = child_key(n.c0, n.lz.x, n.hz.x, as_uint(n.lk.x), q, tmin, tmax);
+    k1 = child_key(n.c1, n.lz.y, n.hz.y, as_uint(n.lk.y), q, tmin, tmax);
+    k2 = child_key(n.c2, n.lz.z, n.hz.z, as_uint(n.lk.z), q, tmin, tmax);
+    k3 = child_key(n.c3, n.lz.w, n.hz.w, as_uint(n.lk.w), q, tmin, tmax);
+    key_exchange(k0, k1), key_exchange(k2, k3), key_exchange(k0, k2), key_exchange(k1, k3), key_exchange(k1, k2);
+}
+// largest key that can still matter once the closest hit is t_best (same conservative bound as slab_node)
+RTB_DEV uint32_t key_limit(float t_best, float pad) { return as_uint(fmaf(t_best, 1.0000004f, pad)) | 0xFFFFu; }
+
+RTB_DEV uint32_t stack4_pop(const uint32_t* stack, int& sp, float t_best, float pad) {
+    const uint32_t limit = key_limit(t_best, pad);
+    while (sp > 0) {
+        const uint32_t k = stack[--sp];
+        if (k <= limit) return k & 0xFFFFu;
+    }
+    return RTB_LINK4_DONE;
+}
+
+// closest_hit over the 4-wide tree (t_min must be > 0: keys compare as unsigned integers)
+RTB_DEV void closest_hit4(const DSceneView& S, const Ray& r, float tmin, float tmax, int origin_prim, int origin_face, float& t_best, int& prim_best,
+                          int& face_best) {
+    t_best = tmax, prim_best = -1, face_best = 0;
+    if (S.n_prims == 0) return;
+    const NodeRay nr = node_ray(r);
+    uint32_t stack[RTB_WIDE_STACK];
+    int sp = 0;
+    uint32_t cur = 0u;  // the root node
+    while (cur != RTB_LINK4_DONE) {
+        if (cur & RTB_LINK4_LEAF) {
+            const int i = (int)(cur & 0x7FFFu);
+            PrimRec p = load_prim(S.prims + i);
+            float t;
+            int face;
+            if (hit_prim(S, p, r, tmin, t_best, i == origin_prim, origin_face, t, face)) t_best = t, prim_best = i, face_best = face;
+            cur = stack4_pop(stack, sp, t_best, nr.pad);
+        } else {
+            uint32_t k0, k1, k2, k3;
+            node4_sorted_keys(node4_fetch(S.nodes4, cur), nr, tmin, t_best, k0, k1, k2, k3);
+            if (k0 == RTB_KEY_MISS) {
+                cur = stack4_pop(stack, sp, t_best, nr.pad);
+            } else {
+                if (k3 != RTB_KEY_MISS) stack[sp++] = k3;
+                if (k2 != RTB_KEY_MISS) stack[sp++] = k2;
+                if (k1 != RTB_KEY_MISS) stack[sp++] = k1;
+                cur = k0 & 0xFFFFu;
             }
         }
     }
@@ -470,7 +583,7 @@ RTB_DEV void sample_media(const DSceneView& S, const Ray& r, float tmin, const f
     float len = sqrtf(dot(r.d, r.d));
     for (int m = 0; m < S.n_media; ++m) {
         const DMedium* M = S.media + m;
-        PrimRec b = load_prim(&M->boundary);
+        PrimRec b = load_prim16(&M->boundary);
         float4 tail = ld4(reinterpret_cast<const char*>(M) + 32);
         float t1, t2;
         if (!medium_interval(S, b, r, tmin, t_best, t1, t2)) continue;
@@ -951,7 +1064,7 @@ RTB_DEV bool wf_shade(const DSceneView& S, const DRenderParams& P, WfSlot& s, V3
 }
 
 // ------------------------------------------------------------------ test entry points (rt_intersect_batch etc.)
-enum { QUERY_BVH = 0, QUERY_LINEAR = 1, QUERY_MEDIUM = 2 };
+enum { QUERY_BVH = 0, QUERY_LINEAR = 1, QUERY_MEDIUM = 2, QUERY_BVH4 = 3 };
 
 // Hittable::hit for one ray given as 8 floats (origin, direction, t_min, t_max) -> RtHit
 RTB_DEV void intersect_query(const DSceneView& S, int mode, const float* q, RtHit& out) {
@@ -962,14 +1075,15 @@ RTB_DEV void intersect_query(const DSceneView& S, int mode, const float* q, RtHi
     out.p[0] = out.p[1] = out.p[2] = 0.f;
     out.normal[0] = out.normal[1] = out.normal[2] = 0.f;
     if (mode == QUERY_MEDIUM) {
-        PrimRec b = load_prim(&S.media[0].boundary);
+        PrimRec b = load_prim16(&S.media[0].boundary);
         float t1, t2;
         if (medium_interval(S, b, r, tmin, tmax, t1, t2)) out.t = t1, out.u = t2, out.material = S.media[0].mat;
         return;
     }
     float t;
     int prim, face;
-    if (mode == QUERY_BVH) closest_hit(S, r, tmin, tmax, -1, 0, t, prim, face);
+    if (mode == QUERY_BVH4 && S.nodes4 && tmin > 0.0f) closest_hit4(S, r, tmin, tmax, -1, 0, t, prim, face);
+    else if (mode == QUERY_BVH || mode == QUERY_BVH4) closest_hit(S, r, tmin, tmax, -1, 0, t, prim, face);
     else closest_hit_linear(S, r, tmin, tmax, t, prim, face);
     if (prim < 0) return;
     PrimRec P = load_prim(S.prims + prim);

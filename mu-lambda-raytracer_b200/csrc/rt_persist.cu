@@ -25,7 +25,6 @@
 
 namespace rtb {
 
-#define PS_THREADS 128
 #define PS_DONE RTB_TRAVERSAL_DONE
 #define PS_MIN_DESCEND 6   // lanes that must still be descending inner nodes for the inner loop to keep going
 #define PS_LEAVE 8         // lanes that must have finished before the warp leaves the traversal loop (to start them on their other path)
@@ -34,9 +33,6 @@ namespace rtb {
 // resident blocks per SM the kernel is compiled for: 6 = 80 registers with 32 B of spills.  Measured on C4:
 // 5 blocks (94 registers, no spills) -4 %, 7 blocks (72 registers, 132 B of spills, only 96 KB of L1 left) -6 %
 #define PS_MIN_BLOCKS 6
-#ifndef PS_SPECULATE
-#define PS_SPECULATE 0  // speculative descent (postponed leaves): evaluated, 1-6 % slower on C4 with one-primitive leaves
-#endif
 #define PS_CHUNK 256u      // camera paths a warp reserves per atomic
 
 enum { ST_EMPTY = 0, ST_TRAV = 1, ST_DONE = 2, ST_READY = 3 };
@@ -50,9 +46,13 @@ struct PsCounters {
     unsigned long long next_path, total_paths, rays;
 };
 
+#define PS_VARIANTS 8
+#define PS_DEFAULT_LAYOUT 4    // RT_BVH_LAYOUT / RtParams.bvh_layout override
+#define PS_DEFAULT_VARIANT 2   // index into kVariants for the 4-wide layout; RT_PS_VARIANT overrides
+#define PS_MAX_SMEM (227u * 1024u)
 struct PersistState {
     PsCounters* ctr = nullptr;
-    int blocks = 0;
+    int blocks[PS_VARIANTS] = {};  // resident grid of each kernel instance (0 = not queried yet)
 };
 
 // One camera path = one record of PS_REC words in shared memory, SoA over the block's threads (conflict-free):
@@ -62,7 +62,8 @@ struct PersistState {
 // flight (ray, node-test constants, closest hit so far, cursor), so shading a parked path moves nothing around.
 enum { R_OX, R_OY, R_OZ, R_DX, R_DY, R_DZ, R_BR, R_BG, R_BB, R_T, R_PIXEL, R_SAMPLE, R_FLAGS, R_ORIGIN, R_HIT, PS_REC };
 #define PS_SLOTS 2
-typedef float PsPool[PS_SLOTS][PS_REC][PS_THREADS];
+// field `f` of record `slot` of the calling thread; the pool is [PS_SLOTS][PS_REC][NT] floats at the start of shared memory
+#define POOL(slot, f) pool[((slot) * PS_REC + (f)) * NT + threadIdx.x]
 
 __device__ __forceinline__ int slot_status(unsigned int stat, int s) { return (int)((stat >> (2 * s)) & 3u); }
 __device__ __forceinline__ unsigned int slot_set(unsigned int stat, int s, int st) { return (stat & ~(3u << (2 * s))) | ((unsigned int)st << (2 * s)); }
@@ -74,21 +75,26 @@ __device__ __forceinline__ int slot_find(unsigned int stat, int want) {  // lowe
     return found;
 }
 
-__device__ __forceinline__ void rec_load(const PsPool& pool, int slot, WfSlot& s) {
-    const unsigned int t = threadIdx.x;
-    const float(*r)[PS_THREADS] = pool[slot];
-    s.A = f4(r[R_OX][t], r[R_OY][t], r[R_OZ][t], r[R_PIXEL][t]);
-    s.B = f4(r[R_DX][t], r[R_DY][t], r[R_DZ][t], r[R_FLAGS][t]);
-    s.C = f4(r[R_BR][t], r[R_BG][t], r[R_BB][t], r[R_SAMPLE][t]);
-    s.D = f4(r[R_T][t], r[R_HIT][t], r[R_ORIGIN][t], 0.f);
+template <int NT>
+__device__ __forceinline__ void rec_load(const float* pool, int slot, WfSlot& s) {
+    s.A = f4(POOL(slot, R_OX), POOL(slot, R_OY), POOL(slot, R_OZ), POOL(slot, R_PIXEL));
+    s.B = f4(POOL(slot, R_DX), POOL(slot, R_DY), POOL(slot, R_DZ), POOL(slot, R_FLAGS));
+    s.C = f4(POOL(slot, R_BR), POOL(slot, R_BG), POOL(slot, R_BB), POOL(slot, R_SAMPLE));
+    s.D = f4(POOL(slot, R_T), POOL(slot, R_HIT), POOL(slot, R_ORIGIN), 0.f);
 }
-__device__ __forceinline__ void rec_store(PsPool& pool, int slot, const WfSlot& s) {
-    const unsigned int t = threadIdx.x;
-    float(*r)[PS_THREADS] = pool[slot];
-    r[R_OX][t] = s.A.x, r[R_OY][t] = s.A.y, r[R_OZ][t] = s.A.z, r[R_PIXEL][t] = s.A.w;
-    r[R_DX][t] = s.B.x, r[R_DY][t] = s.B.y, r[R_DZ][t] = s.B.z, r[R_FLAGS][t] = s.B.w;
-    r[R_BR][t] = s.C.x, r[R_BG][t] = s.C.y, r[R_BB][t] = s.C.z, r[R_SAMPLE][t] = s.C.w;
-    r[R_T][t] = s.D.x, r[R_HIT][t] = s.D.y, r[R_ORIGIN][t] = s.D.z;
+template <int NT>
+__device__ __forceinline__ void rec_store(float* pool, int slot, const WfSlot& s) {
+    POOL(slot, R_OX) = s.A.x, POOL(slot, R_OY) = s.A.y, POOL(slot, R_OZ) = s.A.z, POOL(slot, R_PIXEL) = s.A.w;
+    POOL(slot, R_DX) = s.B.x, POOL(slot, R_DY) = s.B.y, POOL(slot, R_DZ) = s.B.z, POOL(slot, R_FLAGS) = s.B.w;
+    POOL(slot, R_BR) = s.C.x, POOL(slot, R_BG) = s.C.y, POOL(slot, R_BB) = s.C.z, POOL(slot, R_SAMPLE) = s.C.w;
+    POOL(slot, R_T) = s.D.x, POOL(slot, R_HIT) = s.D.y, POOL(slot, R_ORIGIN) = s.D.z;
+}
+
+// 128-bit load from a shared-memory address (the scene copy of the SCENE variants)
+__device__ __forceinline__ float4 lds4(uint32_t saddr) {
+    float4 v;
+    asm("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(saddr));
+    return v;
 }
 
 // Perlin::turbulence (textures.rs:76-88, depth 7) of one point, computed by the whole warp: term = (octave, corner),
@@ -125,8 +131,15 @@ __global__ void ps_reset_kernel(PsCounters* c, unsigned long long total) { c->ne
 enum { PSS_SHADE_PHASES, PSS_SHADE_ACT, PSS_SHADE_DONE, PSS_SHADE_ONPARK, PSS_EXT_PHASES, PSS_INNER_ITERS, PSS_INNER_LANES, PSS_LEAF_STEPS,
        PSS_LEAF_LANES, PSS_LEAF_PRIMS, PSS_EXT_ROUNDS, PSS_EXT_TRAV_LANES, PSS_NOISE, PSS_COUNT };
 
-template <bool STATS>
-__global__ void __launch_bounds__(PS_THREADS, STATS ? 4 : PS_MIN_BLOCKS) persist_kernel(DSceneView S, DCamera cam, DRenderParams P, PsCounters* __restrict__ ctr,
+// WIDE: walk the 4-wide tree (DNode4) with 4-byte stack keys, the first SD stack levels in shared memory (the rest, if a
+// ray ever needs them, in local memory); !WIDE: the binary 32-byte-node tree with (link, distance) entries in local memory.
+// NT threads per block.  SCENE bit 0: the block keeps a copy of the DNode4 array in shared memory, bit 1: of the
+// primitives — ONE large block per SM then shares a single copy, and the L1 that is left holds only what is not copied.
+// Dynamic shared memory: [pool PS_SLOTS x PS_REC x NT floats][stack SD x NT keys][nodes4][prims].
+#define PS_SCENE_NODES 1
+#define PS_SCENE_PRIMS 2
+template <bool STATS, bool WIDE, int SD, int NT, int SCENE>
+__global__ void __launch_bounds__(NT, (STATS || NT > 128) ? 1 : PS_MIN_BLOCKS) persist_kernel(DSceneView S, DCamera cam, DRenderParams P, PsCounters* __restrict__ ctr,
                                                              float* __restrict__ accum, unsigned long long* __restrict__ rays_out,
                                                              unsigned int chunk_size, unsigned long long* __restrict__ stats, PsTune tune) {
     unsigned int st_[PSS_COUNT];
@@ -137,10 +150,31 @@ __global__ void __launch_bounds__(PS_THREADS, STATS ? 4 : PS_MIN_BLOCKS) persist
         const unsigned int v_ = (unsigned int)(v); \
         if (lane == 0) st_[k] += v_;               \
     }
-    __shared__ PsPool pool;
+    extern __shared__ float4 smem_raw[];
+    float* const pool = reinterpret_cast<float*>(smem_raw);
+    uint32_t* const sstack = reinterpret_cast<uint32_t*>(pool + PS_SLOTS * PS_REC * NT);  // [SD][NT], conflict-free
+    uint32_t nodes_saddr = 0u, prims_saddr = 0u;
+    if constexpr (SCENE != 0) {
+        float4* dst = reinterpret_cast<float4*>(sstack + SD * NT);
+        if (SCENE & PS_SCENE_NODES) {
+            const float4* src = reinterpret_cast<const float4*>(S.nodes4);
+            const int n16 = S.n_nodes4 * (int)(sizeof(DNode4) / 16);
+            for (int i = threadIdx.x; i < n16; i += NT) dst[i] = __ldg(src + i);
+            nodes_saddr = (uint32_t)__cvta_generic_to_shared(dst);
+            dst += n16;
+        }
+        if (SCENE & PS_SCENE_PRIMS) {
+            const float4* src = reinterpret_cast<const float4*>(S.prims);
+            const int n16 = S.n_prims * (int)(sizeof(DPrim) / 16);
+            for (int i = threadIdx.x; i < n16; i += NT) dst[i] = __ldg(src + i);
+            prims_saddr = (uint32_t)__cvta_generic_to_shared(dst);
+        }
+        __syncthreads();
+    }
     const unsigned int lane = threadIdx.x & 31u;
     const unsigned int lt_mask = (1u << lane) - 1u;
-    const int root_link = S.n_prims > 0 ? (int)as_uint(ld4(S.nodes).w) : PS_DONE;
+    constexpr int DONE = WIDE ? (int)RTB_LINK4_DONE : PS_DONE;
+    const int root_link = S.n_prims > 0 ? (WIDE ? 0 : (int)as_uint(ld4(S.nodes).w)) : DONE;
     const unsigned long long total = ctr->total_paths;
     const unsigned int npix = (unsigned int)P.width * (unsigned int)P.height;
 
@@ -152,9 +186,23 @@ __global__ void __launch_bounds__(PS_THREADS, STATS ? 4 : PS_MIN_BLOCKS) persist
     NodeRay nr;
     nr.inv = nr.noi = v3(0.f, 0.f, 0.f), nr.pad = 0.f;
     float t_best = 0.f;
-    int hit = -1, origin_prim = -1, origin_face = 0, cur = PS_DONE, sp = 0;
-    int pend = 0;  // a leaf reached but not tested yet (leaf links are negative, 0 = none): see the extend phase
-    StackEntry stack[RTB_BVH_STACK];  // (node link, entry distance of its box): see stack_pop
+    int hit = -1, origin_prim = -1, origin_face = 0, cur = DONE, sp = 0;
+    StackEntry stack[WIDE ? 1 : RTB_BVH_STACK];  // binary tree: (node link, entry distance of its box), see stack_pop
+    uint32_t lstack[WIDE ? RTB_WIDE_STACK : 1];  // 4-wide tree: the keys above the shared-memory levels
+    auto push4 = [&](uint32_t k) {
+        if (SD > 0 && sp < SD) sstack[sp * NT + threadIdx.x] = k;
+        else lstack[sp - SD] = k;
+        sp += 1;
+    };
+    auto pop4 = [&]() -> int {
+        const uint32_t limit = key_limit(t_best, nr.pad);
+        while (sp > 0) {
+            sp -= 1;
+            const uint32_t k = (SD > 0 && sp < SD) ? sstack[sp * NT + threadIdx.x] : lstack[sp - SD];
+            if (k <= limit) return (int)(k & 0xFFFFu);
+        }
+        return DONE;
+    };
     // warp-uniform reservation of camera-path numbers
     unsigned long long chunk_next = 0, chunk_end = 0;
     uint32_t chunk_pixel = 0, chunk_sample = 0;  // (pixel, sample) of path chunk_next
@@ -166,13 +214,11 @@ __global__ void __launch_bounds__(PS_THREADS, STATS ? 4 : PS_MIN_BLOCKS) persist
         if (tslot < 0) {
             const int sl = slot_find(stat, ST_READY);
             if (sl >= 0) {
-                const unsigned int t = threadIdx.x;
-                const float(*q)[PS_THREADS] = pool[sl];
-                r.o = v3(q[R_OX][t], q[R_OY][t], q[R_OZ][t]), r.d = v3(q[R_DX][t], q[R_DY][t], q[R_DZ][t]);
-                t_best = q[R_T][t], hit = __float_as_int(q[R_HIT][t]), origin_prim = __float_as_int(q[R_ORIGIN][t]);
-                origin_face = (int)((__float_as_uint(q[R_FLAGS][t]) >> WF_FACE_SHIFT) & 7u);
+                r.o = v3(POOL(sl, R_OX), POOL(sl, R_OY), POOL(sl, R_OZ)), r.d = v3(POOL(sl, R_DX), POOL(sl, R_DY), POOL(sl, R_DZ));
+                t_best = POOL(sl, R_T), hit = __float_as_int(POOL(sl, R_HIT)), origin_prim = __float_as_int(POOL(sl, R_ORIGIN));
+                origin_face = (int)((__float_as_uint(POOL(sl, R_FLAGS)) >> WF_FACE_SHIFT) & 7u);
                 nr = node_ray(r);
-                cur = root_link, sp = 0, pend = 0;
+                cur = root_link, sp = 0;
                 tslot = sl;
                 stat = slot_set(stat, sl, ST_TRAV);
             }
@@ -201,7 +247,7 @@ __global__ void __launch_bounds__(PS_THREADS, STATS ? 4 : PS_MIN_BLOCKS) persist
             WfSlot s;
             if (shade) {
                 n_rays += 1u;
-                rec_load(pool, s_work, s);
+                rec_load<NT>(pool, s_work, s);
                 pixel_out = __float_as_uint(s.A.w);
                 alive = wf_shade_core(S, P, s, radiance, &req, segment_next);
             }
@@ -270,7 +316,7 @@ __global__ void __launch_bounds__(PS_THREADS, STATS ? 4 : PS_MIN_BLOCKS) persist
             if (act) {
                 if (alive) {
                     wf_presample_media(S, P, s, segment_next);
-                    rec_store(pool, s_work, s);
+                    rec_store<NT>(pool, s_work, s);
                     stat = slot_set(stat, s_work, ST_READY);
                 } else {
                     stat = slot_set(stat, s_work, ST_EMPTY);
@@ -286,80 +332,91 @@ __global__ void __launch_bounds__(PS_THREADS, STATS ? 4 : PS_MIN_BLOCKS) persist
             PS_STAT(PSS_EXT_ROUNDS, 1)
             PS_STAT(PSS_EXT_TRAV_LANES, __popc(__ballot_sync(0xffffffffu, has)))
             // (a) inner nodes: lanes leave the loop when they reach a leaf or run out of nodes
-            while (has && cur >= 0) {
+            while (has && (WIDE ? (cur & (int)RTB_LINK4_LEAF) == 0 : cur >= 0)) {
                 if (STATS) {
                     const unsigned int am = __activemask();
                     if ((int)lane == __ffs((int)am) - 1) st_[PSS_INNER_ITERS] += 1u, st_[PSS_INNER_LANES] += (unsigned int)__popc(am);
                 }
-                const char* base = reinterpret_cast<const char*>(S.nodes + cur);
-                float4 l0 = ld4(base), l1 = ld4(base + 16), r0 = ld4(base + 32), r1 = ld4(base + 48);
-                float tl, tr;
-                bool hl = slab_node(l0, l1, nr, RTB_T_MIN, t_best, tl);
-                bool hr = slab_node(r0, r1, nr, RTB_T_MIN, t_best, tr);
-                int ll = (int)as_uint(l0.w), lr = (int)as_uint(r0.w);
-                if (hl && hr) {
-                    bool left_first = tl <= tr;
-                    stack[sp].node = left_first ? lr : ll, stack[sp].tn = left_first ? tr : tl;
-                    sp += 1;
-                    cur = left_first ? ll : lr;
-                } else if (hl) {
-                    cur = ll;
-                } else if (hr) {
-                    cur = lr;
+                if constexpr (WIDE) {
+                    uint32_t k0, k1, k2, k3;
+                    Node4Regs n4;
+                    if constexpr ((SCENE & PS_SCENE_NODES) != 0) {
+                        const uint32_t a = nodes_saddr + (uint32_t)cur * (uint32_t)sizeof(DNode4);
+                        n4.c0 = lds4(a), n4.c1 = lds4(a + 16), n4.c2 = lds4(a + 32), n4.c3 = lds4(a + 48);
+                        n4.lz = lds4(a + 64), n4.hz = lds4(a + 80), n4.lk = lds4(a + 96);
+                    } else {
+                        n4 = node4_fetch(S.nodes4, (uint32_t)cur);
+                    }
+                    node4_sorted_keys(n4, nr, RTB_T_MIN, t_best, k0, k1, k2, k3);
+                    if (k0 == RTB_KEY_MISS) {
+                        cur = pop4();
+                    } else {
+                        if (k3 != RTB_KEY_MISS) push4(k3);
+                        if (k2 != RTB_KEY_MISS) push4(k2);
+                        if (k1 != RTB_KEY_MISS) push4(k1);
+                        cur = (int)(k0 & 0xFFFFu);
+                    }
                 } else {
-                    cur = stack_pop(stack, sp, t_best, nr.pad);
+                    const char* base = reinterpret_cast<const char*>(S.nodes + cur);
+                    const F8 ln = ld8(base), rn = ld8(base + 32);
+                    const float4 l0 = ln.lo, l1 = ln.hi, r0 = rn.lo, r1 = rn.hi;
+                    float tl, tr;
+                    bool hl = slab_node(l0, l1, nr, RTB_T_MIN, t_best, tl);
+                    bool hr = slab_node(r0, r1, nr, RTB_T_MIN, t_best, tr);
+                    int ll = (int)as_uint(l0.w), lr = (int)as_uint(r0.w);
+                    if (hl && hr) {
+                        bool left_first = tl <= tr;
+                        stack[sp].node = left_first ? lr : ll, stack[sp].tn = left_first ? tr : tl;
+                        sp += 1;
+                        cur = left_first ? ll : lr;
+                    } else if (hl) {
+                        cur = ll;
+                    } else if (hr) {
+                        cur = lr;
+                    } else {
+                        cur = stack_pop(stack, sp, t_best, nr.pad);
+                    }
                 }
-#if PS_SPECULATE
-                // speculative descent (Aila & Laine): the first leaf a lane reaches is postponed and the lane keeps
-                // descending with the next node of its stack, so that the inner-node loop and the leaf step both run
-                // with more lanes; the price is a few node visits the postponed hit would have culled
-                if (cur < 0 && cur != PS_DONE && pend == 0) {
-                    pend = cur;
-                    cur = stack_pop(stack, sp, t_best, nr.pad);
-                }
-#endif
                 if (__popc(__activemask()) < tune.descend) break;
             }
             __syncwarp();
             // (b) one leaf per lane: every primitive of it
-#if PS_SPECULATE
-            const int leaf = has ? pend : 0;
-#else
-            const int leaf = (has && cur < 0 && cur != PS_DONE) ? cur : 0;
-#endif
+            const bool at_leaf = has && cur != DONE && (WIDE ? (cur & (int)RTB_LINK4_LEAF) != 0 : cur < 0);
             if (STATS) {
-                const unsigned int lm = __ballot_sync(0xffffffffu, leaf != 0);
+                const unsigned int lm = __ballot_sync(0xffffffffu, at_leaf);
                 PS_STAT(PSS_LEAF_STEPS, lm != 0u)
                 PS_STAT(PSS_LEAF_LANES, __popc(lm))
             }
-            if (leaf != 0) {
-                int v = ~leaf;
-                int first = v & 0xFFFFFF, count = v >> 24;
+            if (at_leaf) {
+                int first, count;
+                if (WIDE) {
+                    first = cur & 0x7FFF, count = 1;
+                } else {
+                    const int v = ~cur;
+                    first = v & 0xFFFFFF, count = v >> 24;
+                }
                 if (STATS) st_[PSS_LEAF_PRIMS] += (unsigned int)count;
                 for (int i = first; i < first + count; ++i) {
-                    PrimRec q = load_prim(S.prims + i);
+                    PrimRec q;
+                    if constexpr ((SCENE & PS_SCENE_PRIMS) != 0) {
+                        const uint32_t a = prims_saddr + (uint32_t)i * (uint32_t)sizeof(DPrim);
+                        q = prim_from(lds4(a), lds4(a + 16));
+                    } else {
+                        q = load_prim(S.prims + i);
+                    }
                     float t;
                     int face;
                     if (hit_prim(S, q, r, RTB_T_MIN, t_best, i == origin_prim, origin_face, t, face))
                         t_best = t, hit = i | (face << 24);  // closer than the pre-sampled medium event, which it replaces
                 }
-#if PS_SPECULATE
-                pend = 0;
-#else
-                cur = stack_pop(stack, sp, t_best, nr.pad);
-#endif
+                if constexpr (WIDE) cur = pop4();
+                else cur = stack_pop(stack, sp, t_best, nr.pad);
             }
-#if PS_SPECULATE
-            if (has && cur < 0 && cur != PS_DONE) {  // the lane stopped at a second leaf: it becomes the postponed one
-                pend = cur;
-                cur = stack_pop(stack, sp, t_best, nr.pad);
-            }
-#endif
             __syncwarp();
-            if (has && cur == PS_DONE && pend == 0) {  // traversal finished: the hit record goes back to the path's slot
+            if (has && cur == DONE) {  // traversal finished: the hit record goes back to the path's slot
                 has = false;
-                pool[tslot][R_T][threadIdx.x] = t_best;
-                pool[tslot][R_HIT][threadIdx.x] = __int_as_float(hit);
+                POOL(tslot, R_T) = t_best;
+                POOL(tslot, R_HIT) = __int_as_float(hit);
                 stat = slot_set(stat, tslot, ST_DONE);
                 tslot = -1;
             }
@@ -391,32 +448,89 @@ void free_persist(RtScene* s) {
 
 bool persist_supports(const RtScene* s, const RtParams* p) { return p->max_depth <= WF_DEPTH_MASK && s->flat.prims.size() < (1u << 24); }
 
+namespace {
+
+typedef void (*PersistFn)(DSceneView, DCamera, DRenderParams, PsCounters*, float*, unsigned long long*, unsigned int, unsigned long long*, PsTune);
+struct Variant {
+    int layout, smem_stack, threads, scene;
+    PersistFn fn, fn_stats;
+    const char* name;
+};
+#define PS_INSTANCE(wide, sd, nt, scene) persist_kernel<false, wide, sd, nt, scene>, persist_kernel<true, wide, sd, nt, scene>
+// The kernel instances the library carries.  Measured on C4 (profiles/r2_ab_variants.txt): [1] is +1.6 % over [0], [2]
+// (one 768-thread block per SM instead of six 128-thread blocks: 5 KB more L1, one pool) another +1.8 %.
+// RTB_PS_EXPERIMENTS adds the rejected placements (stack levels or scene copies in shared memory: -2 ... -9 %, the L1
+// they take away costs more than the shared-memory latency wins) so that the A/B stays reproducible
+// (tools/experiments/build_experiments.sh); the product build does not carry them.
+const Variant kVariants[] = {
+    {2, 0, 128, 0, PS_INSTANCE(false, 0, 128, 0), "bvh2, 6 x 128 threads per SM"},  // north_star's 32-byte-node binary tree
+    {4, 0, 128, 0, PS_INSTANCE(true, 0, 128, 0), "bvh4, 6 x 128 threads per SM"},
+    {4, 0, 768, 0, PS_INSTANCE(true, 0, 768, 0), "bvh4, 1 x 768 threads per SM"},
+#ifdef RTB_PS_EXPERIMENTS
+    {4, 8, 128, 0, PS_INSTANCE(true, 8, 128, 0), "bvh4, 6 x 128 threads, 8 stack levels in shared memory"},
+    {4, 0, 768, 1, PS_INSTANCE(true, 0, 768, 1), "bvh4, 1 x 768 threads, nodes in shared memory"},
+    {4, 0, 768, 2, PS_INSTANCE(true, 0, 768, 2), "bvh4, 1 x 768 threads, primitives in shared memory"},
+    {4, 0, 768, 3, PS_INSTANCE(true, 0, 768, 3), "bvh4, 1 x 768 threads, nodes + primitives in shared memory"},
+    {4, 0, 640, 3, PS_INSTANCE(true, 0, 640, 3), "bvh4, 1 x 640 threads, nodes + primitives in shared memory"},
+#endif
+};
+const int kNumVariants = (int)(sizeof(kVariants) / sizeof(kVariants[0]));
+static_assert(sizeof(kVariants) / sizeof(kVariants[0]) <= PS_VARIANTS, "PersistState::blocks is too small");
+
+size_t variant_smem(const Variant& V, const RtScene* s) {
+    size_t bytes = (size_t)PS_SLOTS * PS_REC * V.threads * sizeof(float) + (size_t)V.smem_stack * V.threads * sizeof(uint32_t);
+    if (V.scene & PS_SCENE_NODES) bytes += s->flat.nodes4.size() * sizeof(DNode4);
+    if (V.scene & PS_SCENE_PRIMS) bytes += s->flat.prims.size() * sizeof(DPrim);
+    return bytes;
+}
+
+int pick_variant(const RtScene* s, const RtParams* p) {
+    int layout = p->bvh_layout;
+    if (layout == 0)
+        if (const char* e = getenv("RT_BVH_LAYOUT")) layout = atoi(e);
+    if (layout == 0) layout = PS_DEFAULT_LAYOUT;
+    if (layout != 2 && s->flat.nodes4.empty()) layout = 2;  // the scene does not fit the 16-bit links of the wide tree
+    if (layout == 2) return 0;
+    int vi = PS_DEFAULT_VARIANT;
+    if (const char* e = getenv("RT_PS_VARIANT")) vi = std::max(1, std::min(kNumVariants - 1, atoi(e)));
+    if (variant_smem(kVariants[vi], s) > PS_MAX_SMEM) vi = 1;  // the scene copy does not fit beside the path pool
+    return vi;
+}
+
+}  // namespace
+
+int persist_layout_used(const RtScene* s, const RtParams* p) { return kVariants[pick_variant(s, p)].layout; }
+
 int launch_persist(RtScene* s, const DCamera& cam, const RtParams* p, int begin, int count, float* d_accum, cudaStream_t stream, RtProgressFn cb,
                    void* user, int* launches) {
     if (!persist_supports(s, p)) return set_error(RT_ERR_UNSUPPORTED, "persistent pipeline: max_depth above %d or more than 2^24 primitives", WF_DEPTH_MASK);
+    if (p->bvh_layout != 0 && p->bvh_layout != 2 && p->bvh_layout != 4) return set_error(RT_ERR_INVALID, "render: bvh_layout must be 0 (auto), 2 or 4");
     if (p->max_depth <= 0) return RT_OK;  // every path returns Color::ZERO at once (raytrace.rs:87-89)
     if (!s->ps) {
-        PersistState* w = new PersistState();
-        s->ps = w;
-        CU_TRY(rtb::cache_malloc((void**)&w->ctr, sizeof(PsCounters)));
+        s->ps = new PersistState();
+        CU_TRY(rtb::cache_malloc((void**)&s->ps->ctr, sizeof(PsCounters)));
+    }
+    PersistState* w = s->ps;
+    const int vi = pick_variant(s, p);
+    const Variant& V = kVariants[vi];
+    const size_t smem = variant_smem(V, s);
+    const int NT = V.threads;
+    if (w->blocks[vi] == 0) {
         int per_sm = 0, sms = 0;
-        CU_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, persist_kernel<false>, PS_THREADS, 0));
+        for (PersistFn f : {V.fn, V.fn_stats}) CU_TRY(cudaFuncSetAttribute(f, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        CU_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, V.fn, NT, smem));
+        if (per_sm < 1) return set_error(RT_ERR_CUDA, "persistent pipeline: kernel instance '%s' does not fit an SM", V.name);
         if (const char* e = getenv("RT_PS_BLOCKS_PER_SM")) per_sm = std::min(per_sm, std::max(1, atoi(e)));
         // Ask for exactly the shared memory the resident blocks need (+1 KB per block the runtime reserves); whatever is left
         // of the SM's 228 KB is L1, which holds the BVH, the primitives and the traversal stacks.  The driver's
         // default carve-out was larger than needed and cost 5 % (L1 hit rate 92 %).
-        {
-            cudaFuncAttributes fa;
-            CU_TRY(cudaFuncGetAttributes(&fa, persist_kernel<false>));
-            int need_kb = (int)((std::max(1, per_sm) * (fa.sharedSizeBytes + 1024) + 1023) / 1024);
-            int percent = std::min(100, (need_kb * 100 + 227) / 228);
-            if (const char* e = getenv("RT_PS_CARVEOUT")) percent = atoi(e);
-            CU_TRY(cudaFuncSetAttribute(persist_kernel<false>, cudaFuncAttributePreferredSharedMemoryCarveout, percent));
-        }
+        int need_kb = (int)((per_sm * (smem + 1024) + 1023) / 1024);
+        int percent = std::min(100, (need_kb * 100 + 227) / 228);
+        if (const char* e = getenv("RT_PS_CARVEOUT")) percent = atoi(e);
+        CU_TRY(cudaFuncSetAttribute(V.fn, cudaFuncAttributePreferredSharedMemoryCarveout, percent));
         CU_TRY(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, s->device));
-        w->blocks = std::max(1, per_sm) * std::max(1, sms);  // persistent: exactly what is co-resident
+        w->blocks[vi] = per_sm * std::max(1, sms);  // persistent: exactly what is co-resident
     }
-    PersistState* w = s->ps;
     const unsigned long long npix = (unsigned long long)p->width * p->height;
     // one launch = up to 2^29 camera paths when progress is reported (a quarter of a second on C4), 2^33 otherwise: every
     // launch ends with a tail in which the longest paths run on a mostly idle machine
@@ -426,9 +540,9 @@ int launch_persist(RtScene* s, const DCamera& cam, const RtParams* p, int begin,
         int samples = std::min(count - done, samples_per_launch);
         unsigned long long total = npix * (unsigned long long)samples;
         DRenderParams P = device_params(p, begin + done, 1, 1);
-        int blocks = (int)std::min<unsigned long long>((unsigned long long)w->blocks, (total + 2 * PS_THREADS - 1) / (2 * PS_THREADS));
+        int blocks = (int)std::min<unsigned long long>((unsigned long long)w->blocks[vi], (total + 2 * NT - 1) / (2 * NT));
         // small jobs: smaller reservations so that every warp gets work
-        unsigned long long per_warp = total / ((unsigned long long)blocks * (PS_THREADS / 32) * 4ull);
+        unsigned long long per_warp = total / ((unsigned long long)blocks * (NT / 32) * 4ull);
         unsigned int chunk = (unsigned int)std::min<unsigned long long>(PS_CHUNK, std::max<unsigned long long>(32ull, per_warp));
         chunk = (unsigned int)std::min<unsigned long long>(chunk, std::max<unsigned long long>(1ull, npix));
         ps_reset_kernel<<<1, 1, 0, stream>>>(w->ctr, total);
@@ -441,18 +555,18 @@ int launch_persist(RtScene* s, const DCamera& cam, const RtParams* p, int begin,
             unsigned long long* d_stats = nullptr;
             CU_TRY(cudaMalloc(&d_stats, PSS_COUNT * sizeof(unsigned long long)));
             CU_TRY(cudaMemsetAsync(d_stats, 0, PSS_COUNT * sizeof(unsigned long long), stream));
-            persist_kernel<true><<<blocks, PS_THREADS, 0, stream>>>(s->view, cam, P, w->ctr, d_accum, s->d_rays, chunk, d_stats, tune);
+            V.fn_stats<<<blocks, NT, smem, stream>>>(s->view, cam, P, w->ctr, d_accum, s->d_rays, chunk, d_stats, tune);
             unsigned long long h[PSS_COUNT];
             CU_TRY(cudaMemcpyAsync(h, d_stats, sizeof h, cudaMemcpyDeviceToHost, stream));
             CU_TRY(cudaStreamSynchronize(stream));
             cudaFree(d_stats);
             static const char* names[PSS_COUNT] = {"shade_phases", "shade_act_lanes", "shade_done_lanes", "shade_onpark_lanes", "ext_phases", "inner_iters",
                                                    "inner_lanes", "leaf_steps", "leaf_lanes", "leaf_prims", "ext_rounds", "ext_trav_lanes", "noise_evals"};
-            fprintf(stderr, "persist stats (%llu paths):", total);
+            fprintf(stderr, "persist stats [%s] (%llu paths):", V.name, total);
             for (int k = 0; k < PSS_COUNT; ++k) fprintf(stderr, " %s=%llu", names[k], h[k]);
             fprintf(stderr, "\n");
         } else {
-            persist_kernel<false><<<blocks, PS_THREADS, 0, stream>>>(s->view, cam, P, w->ctr, d_accum, s->d_rays, chunk, nullptr, tune);
+            V.fn<<<blocks, NT, smem, stream>>>(s->view, cam, P, w->ctr, d_accum, s->d_rays, chunk, nullptr, tune);
         }
         CU_TRY(cudaGetLastError());
         *launches += 2;

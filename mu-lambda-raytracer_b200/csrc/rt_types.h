@@ -21,6 +21,24 @@ struct alignas(16) DNode {
     int32_t b;  // inner: 0;  leaf: primitive count (informational)
 };
 
+// ---- 4-wide BVH node, 128 B (one cache line): the binary tree collapsed so that a ray takes half as many dependent
+// fetch steps and every step tests four independent boxes.  Child c: xy[c] = (lo.x, lo.y, hi.x, hi.y), loz[c], hiz[c].
+// link[c]: 16-bit child link in the low half — bit 15 clear = index of an inner DNode4, bit 15 set = ONE primitive
+// (index in the low 15 bits) — or RTB_LINK4_EMPTY (all ones) for an unused slot.  The upper half of a used link is
+// zero, so that (bits(t_entry) & 0xFFFF0000) | link is directly the 4-byte sort/stack key of rt_device.cuh.
+struct alignas(16) DNode4 {
+    float xy[4][4];
+    float loz[4];
+    float hiz[4];
+    uint32_t link[4];
+    uint32_t pad[4];
+};
+#define RTB_LINK4_EMPTY 0xFFFFFFFFu
+#define RTB_LINK4_LEAF 0x8000u
+#define RTB_LINK4_DONE 0xFFFFu   // cursor value "traversal finished" (leaf bit set, primitive 0x7FFF is never used)
+#define RTB_WIDE_MAX_NODES 32768
+#define RTB_WIDE_MAX_PRIMS 32767
+
 enum { PRIM_SPHERE = 0, PRIM_BOX = 1 };
 enum {
     PRIM_KIND_MASK = 0x3,
@@ -99,6 +117,7 @@ struct DCamera {  // camera.rs:3-12, computed on the host in f64 by Camera::new'
 #define RTB_PERLIN_POINTS 1024
 #define RTB_MAX_MEDIA 4
 #define RTB_BVH_STACK 48
+#define RTB_WIDE_STACK 64   // 4-byte keys of the 4-wide traversal (flatten.cpp falls back to the binary tree beyond it)
 #define RTB_BIG_SPHERE_RADIUS 100.0
 
 struct DImage {
@@ -109,6 +128,7 @@ struct DImage {
 // what every kernel receives by value
 struct DSceneView {
     const DNode* nodes;
+    const DNode4* nodes4;  // 4-wide collapse of `nodes` (nullptr when the scene exceeds the 16-bit links)
     const DPrim* prims;
     const DBigSphere* big;
     const DInstance* inst;
@@ -118,7 +138,7 @@ struct DSceneView {
     const float* perlin_vec;          // n_perlin x 1024 x 4 floats (xyz, pad)
     const unsigned short* perlin_perm;  // n_perlin x 3 x 1024
     const DImage* images;
-    int32_t n_nodes, n_prims, n_media, n_perlin;
+    int32_t n_nodes, n_nodes4, n_prims, n_media, n_perlin;
     int32_t bg_kind;
     float bg_top[3];
     float bg_bottom[3];

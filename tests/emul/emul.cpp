@@ -27,7 +27,7 @@ static void make_view(EmulScene& e) {
     e.images.clear();
     for (auto& im : f.images) e.images.push_back(DImage{(unsigned long long)(uintptr_t)im.rgba.data(), im.width, im.height});
     DSceneView& v = e.view;
-    v.nodes = f.nodes.data(), v.prims = f.prims.data(), v.big = f.big.data(), v.inst = f.inst.data();
+    v.nodes = f.nodes.data(), v.nodes4 = f.nodes4.empty() ? nullptr : f.nodes4.data(), v.n_nodes4 = (int)f.nodes4.size(), v.prims = f.prims.data(), v.big = f.big.data(), v.inst = f.inst.data();
     v.mats = f.mats.data(), v.texs = f.texs.data(), v.media = f.media.data();
     v.perlin_vec = f.perlin_vec.data(), v.perlin_perm = f.perlin_perm.data(), v.images = e.images.data();
     v.n_nodes = (int)f.nodes.size(), v.n_prims = (int)f.prims.size(), v.n_media = (int)f.media.size();
@@ -58,6 +58,10 @@ void emul_scene_info(void* h, int32_t* n_prims, int32_t* n_nodes, int32_t* n_med
     EmulScene* e = (EmulScene*)h;
     *n_prims = (int)e->flat.prims.size(), *n_nodes = (int)e->flat.nodes.size(), *n_media = (int)e->flat.media.size();
     *depth = e->flat.bvh_depth;
+}
+void emul_scene_info4(void* h, int32_t* n_nodes4, int32_t* depth4) {
+    EmulScene* e = (EmulScene*)h;
+    *n_nodes4 = (int)e->flat.nodes4.size(), *depth4 = e->flat.bvh4_depth;
 }
 int32_t emul_prim_nodes(void* h, int32_t* out, int32_t cap) {
     EmulScene* e = (EmulScene*)h;

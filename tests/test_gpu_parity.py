@@ -60,16 +60,18 @@ def check_hits(g, o, rays, grazing=0.02, tol=1e-5):
     assert ff.sum() <= len(rays) // 20000
 
 
+@pytest.mark.parametrize("layout", [2, 4])
 @pytest.mark.parametrize("name", list(RAY_BOXES))
-def test_closest_hit_matches_oracle(name):
-    rng = np.random.default_rng(abs(hash(name)) % 1000)
+def test_closest_hit_matches_oracle(name, layout):
+    """whole-world closest hit through the binary (32-byte nodes) and the 4-wide (128-byte nodes) BVH"""
+    rng = np.random.default_rng(sum(map(ord, name)) % 1000)
     desc = rt.World(name).build(42)
     scene = rt.Scene(desc)
     ow = S.OracleWorld(name, 42)
     lo, hi, aim, spread = RAY_BOXES[name]
     n = 1_000_000 if name in ("random", "final_scene", "cornell_smoke") else 200_000
     rays = S.random_rays(n, rng, lo, hi, target=aim, spread=spread)
-    g = gpu_intersect(scene, rays)
+    g = gpu_intersect(scene, rays, node=-1 if layout == 2 else -2)
     o = ow.hit(rays)
     check_hits(g, o, rays)
     scene.close()
