@@ -29,7 +29,7 @@
 extern "C" {
 #endif
 
-#define RT_B200_ABI_VERSION 1
+#define RT_B200_ABI_VERSION 2
 
 /* ---- status codes (replace the reference's unwrap()/panic!()) ---- */
 enum {
@@ -140,14 +140,14 @@ typedef struct RtCamera {
 /*
  * RT_PIPELINE_WAVEFRONT      generate / extend / shade as separate kernels over a pool of in-flight paths, with
  *                            per-material-class queues and ballot/prefix-sum compaction between the stages
- * RT_PIPELINE_WAVEFRONT_SMEM the same stages inside one persistent kernel, every warp keeping its own path pool and
- *                            queues in shared memory (evaluated alternative)
+ * RT_PIPELINE_WAVEFRONT_SMEM retired experiment (per-warp pools in shared memory, the slowest of the four in round 1;
+ *                            source kept under tools/experiments/); selecting it returns RT_ERR_UNSUPPORTED
  * RT_PIPELINE_MEGAKERNEL     one thread per pixel x run of samples, no queues (the comparator north_star asks for)
  * RT_PIPELINE_PERSISTENT     the wavefront stages inside one resident kernel: two paths per lane (registers + shared
  *                            memory), warp ballots choose between the extend and the shade stage, no global queues
  * RT_PIPELINE_AUTO           the pipeline measured fastest on B200 for the scene
  */
-enum { RT_PIPELINE_AUTO = 0, RT_PIPELINE_MEGAKERNEL = 1, RT_PIPELINE_WAVEFRONT = 2, RT_PIPELINE_WAVEFRONT_SMEM = 3, RT_PIPELINE_PERSISTENT = 4 };
+enum { RT_PIPELINE_AUTO = 0, RT_PIPELINE_MEGAKERNEL = 1, RT_PIPELINE_WAVEFRONT = 2, RT_PIPELINE_WAVEFRONT_SMEM = 3 /* retired: RT_ERR_UNSUPPORTED */, RT_PIPELINE_PERSISTENT = 4 };
 
 /* RenderingParams (raytrace.rs:50-55) + max_depth (main.rs:72) + device-side knobs */
 typedef struct RtParams {
@@ -183,9 +183,26 @@ typedef struct RtStats {
     double device_ms; /* CUDA-event time of the timed region */
     int32_t kernel_launches;
     int32_t pipeline_used;
+    int32_t bvh_layout_used; /* 2 or 4 (RtParams.bvh_layout) */
+    int32_t reserved;
 } RtStats;
 
-typedef void (*RtProgressFn)(int done, int total, void* user);
+/*
+ * The logger closure of Renderer::render (raytrace.rs:174,182): called exactly `total` = image-height times per
+ * render, once for every row index j = 0 .. total-1 in increasing order, on the calling host thread, paced by the
+ * device's progress (a row is reported when the matching share of the samples has been traced).
+ */
+typedef void (*RtProgressFn)(int row, int total, void* user);
+
+/*
+ * Accumulation.  Radiance sums are kept on the device as unsigned 64-bit FIXED-POINT integers with 32 fractional bits
+ * (value = sum * RT_ACCUM_FIXED_ONE).  Integer addition is associative, so an image does not depend on the order in
+ * which the device's reductions land nor on how the samples are split over calls or GPUs: one seed, one image, bit
+ * for bit — as the reference's per-row PCG streams give it (raytrace.rs:179,197).  A sample is clamped to
+ * [0, 2^20] before conversion (NaN counts as 0); the 64-bit sum holds at least 2^11 such extremes per pixel.
+ * The float buffers of the entry points below are these sums converted once (round to nearest).
+ */
+#define RT_ACCUM_FIXED_ONE 4294967296.0
 
 const char* rt_last_error(void);
 int rt_abi_version(void);
@@ -197,6 +214,12 @@ int rt_scene_hash(const RtSceneDesc* desc, uint8_t out[32]);
 /* flatten + build the device BVH + upload.  Replaces World::build's result + World::background. */
 int rt_scene_create(const RtSceneDesc* desc, int device, RtScene** out);
 void rt_scene_destroy(RtScene* scene);
+/*
+ * Destroyed scenes hand their device blocks (tables, scratch images, texture arrays; at most 512 MB per device) to a
+ * per-device free list instead of cudaFree, because freeing stalls for tens of milliseconds on this driver.  This call
+ * returns all of it to the driver (all devices).  Safe at any time; live scenes are not touched.
+ */
+void rt_release_cached_memory(void);
 int rt_scene_info(const RtScene* scene, int32_t* n_prims, int32_t* n_bvh_nodes, int32_t* n_media, int64_t* device_bytes);
 
 /*
@@ -221,6 +244,16 @@ int rt_render_accumulate_device(const RtScene* scene, const RtCamera* cam, const
                                 float* d_accum_rgb, void* stream, RtStats* stats);
 int rt_tonemap_device(const float* d_accum_rgb, int32_t* d_rgb, int32_t n_pixels, int32_t samples_per_pixel,
                       int device, void* stream);
+/*
+ * The same with the library's native fixed-point sums (3*W*H uint64 on the scene's device, ADDED to): what a sharded
+ * render reduces across ranks with an integer sum — exact, so 1 GPU and N GPUs give identical images.
+ */
+int rt_render_accumulate_fixed_device(const RtScene* scene, const RtCamera* cam, const RtParams* params,
+                                      uint64_t* d_accum_fixed, void* stream, RtStats* stats);
+int rt_tonemap_fixed_device(const uint64_t* d_accum_fixed, int32_t* d_rgb, int32_t n_pixels, int32_t samples_per_pixel,
+                            int device, void* stream);
+int rt_accum_fixed_to_float_device(const uint64_t* d_accum_fixed, float* d_accum_rgb, int64_t n_values, int device,
+                                   void* stream);
 
 /*
  * rt_render over several GPUs of one process (the reference's row-parallel rayon loop, raytrace.rs:176-185, becomes

@@ -73,7 +73,8 @@ class RtHit(C.Structure):
 
 class RtStats(C.Structure):
     _fields_ = [("paths", C.c_uint64), ("rays", C.c_uint64), ("device_ms", C.c_double),
-                ("kernel_launches", C.c_int32), ("pipeline_used", C.c_int32)]
+                ("kernel_launches", C.c_int32), ("pipeline_used", C.c_int32), ("bvh_layout_used", C.c_int32),
+                ("reserved", C.c_int32)]
 
 
 class RtWorldInfo(C.Structure):
@@ -101,6 +102,11 @@ PROTOTYPES = {
                                   C.c_void_p, RtProgressFn, C.c_void_p, C.POINTER(RtStats)]),
     "rt_sample_slice": (None, [C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.POINTER(C.c_int32), C.POINTER(C.c_int32)]),
     "rt_tonemap_device": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int32, C.c_int32, C.c_int, C.c_void_p]),
+    "rt_render_accumulate_fixed_device": (C.c_int, [C.c_void_p, C.POINTER(RtCamera), C.POINTER(RtParams), C.c_void_p,
+                                                    C.c_void_p, C.POINTER(RtStats)]),
+    "rt_tonemap_fixed_device": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int32, C.c_int32, C.c_int, C.c_void_p]),
+    "rt_accum_fixed_to_float_device": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int64, C.c_int, C.c_void_p]),
+    "rt_release_cached_memory": (None, []),
     "rt_intersect_batch": (C.c_int, [C.c_void_p, C.c_int32, C.c_void_p, C.c_int64, C.POINTER(RtHit)]),
     "rt_texture_value_batch": (C.c_int, [C.c_void_p, C.c_int32, C.c_void_p, C.c_int64, C.c_void_p]),
     "rt_generate_rays": (C.c_int, [C.POINTER(RtCamera), C.POINTER(RtParams), C.c_void_p, C.c_void_p, C.c_int64,
@@ -113,8 +119,11 @@ PROTOTYPES = {
     "rt_scene_desc_free": (None, [C.POINTER(RtSceneDesc)]),
 }
 
+RT_ACCUM_FIXED_ONE = 4294967296.0
+
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "librt_b200.so")
+# RT_B200_LIB: another build of the same library (A/B measurements of compile-time choices); never a different implementation
+LIB_PATH = os.environ.get("RT_B200_LIB") or os.path.join(_HERE, "librt_b200.so")
 _lib = None
 
 

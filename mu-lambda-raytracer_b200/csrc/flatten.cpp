@@ -145,8 +145,7 @@ class Flattener {
     bool valid_material(int m) { return m >= 0 && m < d->n_materials; }
 
     // build the device record of one primitive node under `chain`; false if the node is not a primitive
-    bool make_prim(int node, const std::vector<Wrapper>& chain, DPrim& p, Box3& box) {
-        const RtNode& n = d->nodes[node];
+    bool make_prim(const RtNode& n, const std::vector<Wrapper>& chain, DPrim& p, Box3& box) {
         std::memset(&p, 0, sizeof p);
         p.mat = n.material;
         box.reset();
@@ -185,10 +184,7 @@ class Flattener {
             lo[ap] = hi[ap] = n.f[4];
             rect_axis = (uint32_t)ap + 1;
         } else if (n.kind == RT_NODE_BLOCK) {
-            for (int i = 0; i < 3; ++i) {
-                lo[i] = n.f[i], hi[i] = n.f[3 + i];
-                if (!(lo[i] <= hi[i])) return fail(RT_ERR_UNSUPPORTED, "Block corners must be ordered (p0 <= p1)");
-            }
+            for (int i = 0; i < 3; ++i) lo[i] = n.f[i], hi[i] = n.f[3 + i];  // ordered: see block_sides for the other case
         } else {
             return false;
         }
@@ -208,25 +204,72 @@ class Flattener {
         return true;
     }
 
-    // resolve a medium boundary: wrappers down to exactly one primitive
-    bool make_boundary(int node, std::vector<Wrapper> chain, DPrim& p) {
-        for (int guard = 0; guard < 64; ++guard) {
-            if (node < 0 || node >= d->n_nodes) return fail(RT_ERR_INVALID, "medium boundary: bad node index");
-            const RtNode& n = d->nodes[node];
-            if (n.kind == RT_NODE_TRANSLATE) {
-                Wrapper w{false, M3::identity(), {n.f[0], n.f[1], n.f[2]}};
-                chain.push_back(w), node = n.first_child;
-            } else if (n.kind == RT_NODE_ROTATE) {
-                Wrapper w{true, rotation_of(n.axis, n.f[0]), {0, 0, 0}};
-                chain.push_back(w), node = n.first_child;
-            } else {
-                Box3 b;
-                if (make_prim(node, chain, p, b)) return true;
-                if (status != RT_OK) return false;
-                return fail(RT_ERR_UNSUPPORTED, "medium boundary must be a single sphere, rect or block (optionally translated/rotated)");
+    // Block::new (shapes.rs:173-186) with corners that are NOT ordered: the reference builds six rects whose bounds go
+    // through AARect::new's one-sided normalisation (aarects.rs:31-43: the second axis keeps its first value as minimum),
+    // so some sides degenerate to a line.  Such a block is flattened as those six rects, not as one slab primitive.
+    static bool block_is_ordered(const RtNode& n) { return n.f[0] <= n.f[3] && n.f[1] <= n.f[4] && n.f[2] <= n.f[5]; }
+    static void block_sides(const RtNode& b, RtNode out6[6]) {
+        const double* p0 = b.f;
+        const double* p1 = b.f + 3;
+        const double sides[6][6] = {
+            {RT_NODE_XYRECT, p0[0], p1[0], p0[1], p1[1], p1[2]}, {RT_NODE_XYRECT, p0[0], p1[0], p0[1], p1[1], p0[2]},
+            {RT_NODE_XZRECT, p0[0], p1[0], p0[2], p1[2], p0[1]}, {RT_NODE_XZRECT, p0[0], p1[0], p0[2], p1[2], p1[1]},
+            {RT_NODE_YZRECT, p0[1], p1[1], p0[2], p1[2], p0[0]}, {RT_NODE_YZRECT, p0[1], p1[1], p0[2], p1[2], p1[0]}};
+        for (int i = 0; i < 6; ++i) {
+            out6[i] = b;
+            out6[i].kind = (int32_t)sides[i][0];
+            for (int k = 0; k < 5; ++k) out6[i].f[k] = sides[i][1 + k];
+        }
+    }
+
+    // the surface primitives below `node` (lists, BVHs and transforms are transparent), appended to prims/boxes
+    bool collect_prims(int node, std::vector<Wrapper>& chain, int depth, std::vector<DPrim>& prims, std::vector<Box3>* boxes, std::vector<int32_t>* nodes_out) {
+        if (status != RT_OK) return false;
+        if (node < 0 || node >= d->n_nodes) return fail(RT_ERR_INVALID, "node index out of range");
+        if (depth > 64) return fail(RT_ERR_INVALID, "description nests deeper than 64 levels (cycle?)");
+        const RtNode& n = d->nodes[node];
+        switch (n.kind) {
+            case RT_NODE_TRANSLATE: {
+                chain.push_back(Wrapper{false, M3::identity(), {n.f[0], n.f[1], n.f[2]}});
+                bool ok = collect_prims(n.first_child, chain, depth + 1, prims, boxes, nodes_out);
+                chain.pop_back();
+                return ok;
+            }
+            case RT_NODE_ROTATE: {
+                if (n.axis < 0 || n.axis > 2) return fail(RT_ERR_INVALID, "rotate axis must be 0, 1 or 2");
+                chain.push_back(Wrapper{true, rotation_of(n.axis, n.f[0]), {0, 0, 0}});
+                bool ok = collect_prims(n.first_child, chain, depth + 1, prims, boxes, nodes_out);
+                chain.pop_back();
+                return ok;
+            }
+            case RT_NODE_BVH:
+            case RT_NODE_LIST: {
+                if (n.first_child < 0 || n.child_count < 0 || n.first_child + n.child_count > d->n_children)
+                    return fail(RT_ERR_INVALID, "list/bvh child range out of bounds");
+                for (int i = 0; i < n.child_count; ++i)
+                    if (!collect_prims(d->children[n.first_child + i], chain, depth + 1, prims, boxes, nodes_out)) return false;
+                return true;
+            }
+            case RT_NODE_MEDIUM: return fail(RT_ERR_UNSUPPORTED, "a constant medium cannot be part of another medium's boundary");
+            default: {
+                RtNode parts[6];
+                int n_parts = 1;
+                parts[0] = n;
+                if (n.kind == RT_NODE_BLOCK && !block_is_ordered(n)) block_sides(n, parts), n_parts = 6;
+                for (int i = 0; i < n_parts; ++i) {
+                    DPrim p;
+                    Box3 b;
+                    if (!make_prim(parts[i], chain, p, b)) {
+                        if (status == RT_OK) fail(RT_ERR_INVALID, "unknown node kind");
+                        return false;
+                    }
+                    prims.push_back(p);
+                    if (boxes) boxes->push_back(b);
+                    if (nodes_out) nodes_out->push_back(node);
+                }
+                return true;
             }
         }
-        return fail(RT_ERR_INVALID, "medium boundary: transform chain too deep");
     }
 
     void walk(int node, std::vector<Wrapper>& chain, int depth) {
@@ -275,26 +318,26 @@ class Flattener {
                     fail(RT_ERR_INVALID, "medium density must be positive");
                     return;
                 }
+                // ConstantMedium's boundary is any Hittable (volumes.rs:7-11): every surface primitive below it
+                std::vector<DPrim> boundary;
+                if (!collect_prims(n.first_child, chain, depth + 1, boundary, nullptr, nullptr)) return;
+                if (boundary.empty()) return;  // an empty boundary is never hit: the medium does nothing
+                if (boundary.size() > 0xFFFF || out.media.size() >= RTB_MAX_MEDIA) {
+                    fail(RT_ERR_UNSUPPORTED, "too many constant media / boundary primitives");
+                    return;
+                }
                 DMedium m{};
-                if (!make_boundary(n.first_child, chain, m.boundary)) return;
+                m.boundary = boundary[0];
                 m.neg_inv_density = (float)(-1.0 / n.f[0]);
                 m.mat = n.material;
-                m.desc_node = node;
+                m.first = (int32_t)out.media_prims.size();
+                m.count = (int32_t)boundary.size();
+                out.media_prims.insert(out.media_prims.end(), boundary.begin(), boundary.end());
                 out.media.push_back(m);
-                if (out.media.size() > RTB_MAX_MEDIA) fail(RT_ERR_UNSUPPORTED, "more than 4 constant media in one scene");
+                out.media_node.push_back(node);
                 break;
             }
-            default: {
-                DPrim p;
-                Box3 b;
-                if (make_prim(node, chain, p, b)) {
-                    out.prims.push_back(p);
-                    out.prim_node.push_back(node);
-                    prim_box.push_back(b);
-                } else if (status == RT_OK) {
-                    fail(RT_ERR_INVALID, "unknown node kind");
-                }
-            }
+            default: collect_prims(node, chain, depth, out.prims, &prim_box, &out.prim_node);
         }
     }
 
@@ -488,6 +531,20 @@ class Flattener {
         if (wide_overflow || 3 * out.bvh4_depth > RTB_WIDE_STACK) out.nodes4.clear(), out.bvh4_depth = 0;
     }
 
+    int checker_depth(int tex, int level) const {  // levels of checker above the deepest leaf; -1 = too deep / cyclic
+        const RtTexture& t = d->textures[tex];
+        if (t.kind != RT_TEX_CHECKER) return 0;
+        if (level >= RTB_CHECKER_DEPTH) return -1;
+        int a = checker_depth(t.a, level + 1), b = checker_depth(t.b, level + 1);
+        return (a < 0 || b < 0) ? -1 : 1 + std::max(a, b);
+    }
+    bool leaf_needs_uv(int tex, int level) const {
+        const RtTexture& t = d->textures[tex];
+        if (t.kind == RT_TEX_IMAGE) return true;
+        if (t.kind != RT_TEX_CHECKER || level >= RTB_CHECKER_DEPTH) return false;
+        return leaf_needs_uv(t.a, level + 1) || leaf_needs_uv(t.b, level + 1);
+    }
+
     bool tables() {
         for (int i = 0; i < d->n_materials; ++i) {
             const RtMaterial& m = d->materials[i];
@@ -514,11 +571,7 @@ class Flattener {
             dt.kind = t.kind, dt.a = t.a, dt.b = t.b, dt.scale = (float)t.scale;
             for (int k = 0; k < 3; ++k) dt.color[k] = (float)t.color[k];
             if (t.kind == RT_TEX_CHECKER) {
-                // Checker<Odd,Even> nests by type in the reference; the device keeps one level (solid or any
-                // non-checker texture on each side), which covers every shipped world.
                 if (t.a < 0 || t.a >= d->n_textures || t.b < 0 || t.b >= d->n_textures) return fail(RT_ERR_INVALID, "checker child out of range");
-                if (d->textures[t.a].kind == RT_TEX_CHECKER || d->textures[t.b].kind == RT_TEX_CHECKER)
-                    return fail(RT_ERR_UNSUPPORTED, "nested checker textures");
             } else if (t.kind == RT_TEX_NOISE) {
                 if (t.a < 0 || t.a >= d->n_perlins) return fail(RT_ERR_INVALID, "noise texture: perlin table out of range");
             } else if (t.kind == RT_TEX_IMAGE) {
@@ -527,6 +580,13 @@ class Flattener {
                 return fail(RT_ERR_INVALID, "unknown texture kind");
             }
             out.texs.push_back(dt);
+        }
+        // Checker<Odd, Even> nests by type in the reference (textures.rs:28-49): the device resolves a chain of checkers
+        // in a loop of at most RTB_CHECKER_DEPTH levels.  DTexture.needs_uv: some leaf below is an image (sphere_uv needed).
+        for (int i = 0; i < d->n_textures; ++i) {
+            int depth = checker_depth(i, 0);
+            if (depth < 0) return fail(RT_ERR_UNSUPPORTED, "checker textures nest deeper than 8 levels (or form a cycle)");
+            out.texs[i].needs_uv = leaf_needs_uv(i, 0) ? 1 : 0;
         }
         for (int i = 0; i < d->n_perlins; ++i) {
             const RtPerlin& p = d->perlins[i];

@@ -18,6 +18,8 @@ struct FlatScene {
     std::vector<DMaterial> mats;    // same indexing as the description
     std::vector<DTexture> texs;     // same indexing as the description
     std::vector<DMedium> media;
+    std::vector<DPrim> media_prims;   // boundary primitives, medium after medium
+    std::vector<int32_t> media_node;  // description node of each medium
     std::vector<float> perlin_vec;           // n x 1024 x 4
     std::vector<unsigned short> perlin_perm; // n x 3 x 1024
     struct Image {

@@ -117,20 +117,23 @@ std::string exe_dir(const char* argv0) {
     return s == std::string::npos ? "." : p.substr(0, s);
 }
 
-struct Progress {  // the logger closure of do_tracing (main.rs:157-173), driven per device pass instead of per row
+struct Progress {  // the logger closure of do_tracing (main.rs:157-173): called once per row, counts the rows down
     std::chrono::steady_clock::time_point start;
     long long last_logged_ms = 0;
+    int remaining = -1;
 };
-void progress_cb(int done, int total, void* user) {
+void progress_cb(int /*row*/, int total, void* user) {
     Progress* p = (Progress*)user;
-    if (done >= total) {
+    if (p->remaining < 0) p->remaining = total;
+    p->remaining -= 1;
+    if (p->remaining == 0) {
         fprintf(stderr, "\r%-50s", "Done!");
         return;
     }
     long long elapsed = std::chrono::duration_cast<std::chrono::milliseconds>(std::chrono::steady_clock::now() - p->start).count();
     if (elapsed - p->last_logged_ms > 300) {
         p->last_logged_ms = elapsed;
-        fprintf(stderr, "\rRemaining: %3d%%  ", (int)((long long)(total - done) * 100 / total));
+        fprintf(stderr, "\rRemaining: %3d%%  ", (int)((long long)p->remaining * 100 / total));
     }
 }
 
@@ -223,7 +226,7 @@ int main(int argc, char** argv) {
     uint64_t render_seed = (opt.count("seed") && !randomized_rendering) ? world_seed : (((uint64_t)rd() << 32) ^ (uint64_t)rd());
     long long gpus = parse_int(opt["gpus"], "gpus");
     static const std::map<std::string, int> pipelines = {{"auto", RT_PIPELINE_AUTO}, {"megakernel", RT_PIPELINE_MEGAKERNEL},
-                                                         {"wavefront", RT_PIPELINE_WAVEFRONT}, {"wavefront_smem", RT_PIPELINE_WAVEFRONT_SMEM},
+                                                         {"wavefront", RT_PIPELINE_WAVEFRONT},
                                                          {"persistent", RT_PIPELINE_PERSISTENT}};
     if (!pipelines.count(opt["pipeline"])) usage_error("'" + opt["pipeline"] + "' isn't a valid value for '--pipeline <pipeline>'");
 

@@ -24,16 +24,16 @@ using namespace rtb;
 // place), a warp covers an 8x4 pixel tile, and the per-thread sum is added to the accumulation buffer with three
 // float reductions.  rays_out counts path segments (warp-aggregated).
 __global__ void __launch_bounds__(128) render_items_kernel(DSceneView S, DCamera cam, DRenderParams P, long long n_items, int total_samples,
-                                                           float* __restrict__ accum, unsigned long long* __restrict__ rays_out) {
+                                                           AccumFx* __restrict__ accum, unsigned long long* __restrict__ rays_out) {
     long long item = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     uint32_t n_rays = 0;
     int px, py, chunk;
     if (item < n_items && item_to_pixel(P, item, px, py, chunk)) {
         int first = chunk * P.samples_per_item;
         int count = min(P.samples_per_item, total_samples - first);
-        float sum[3];
+        AccumFx sum[3];
         integrate_item(S, cam, P, px, py, P.sample_begin + first, count, sum, n_rays);
-        float* dst = accum + 3 * ((size_t)py * P.width + px);
+        AccumFx* dst = accum + 3 * ((size_t)py * P.width + px);
         atomicAdd(dst + 0, sum[0]);
         atomicAdd(dst + 1, sum[1]);
         atomicAdd(dst + 2, sum[2]);
@@ -45,13 +45,27 @@ __global__ void __launch_bounds__(128) render_items_kernel(DSceneView S, DCamera
 
 // to_rgb (raytrace.rs:59-68): gamma 2, clamp, x255.999, truncate.  Done in f64 so that, given the same sums, the
 // bytes are the reference's.
-__global__ void tonemap_kernel(const float* __restrict__ accum, int32_t* __restrict__ rgb, int n_values, double scale) {
-    int i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= n_values) return;
-    double x = sqrt((double)accum[i] * scale);
+__device__ __forceinline__ int32_t to_rgb_f64(double mean) {
+    double x = sqrt(mean);
     x = x < 0.0 ? 0.0 : (x > 0.99999999 ? 0.99999999 : x);  // f64::clamp keeps NaN; `as i32` maps NaN to 0
     double y = 255.999 * x;
-    rgb[i] = (y != y) ? 0 : (int32_t)y;
+    return (y != y) ? 0 : (int32_t)y;
+}
+__global__ void tonemap_kernel(const float* __restrict__ accum, int32_t* __restrict__ rgb, int n_values, double scale) {
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n_values) rgb[i] = to_rgb_f64((double)accum[i] * scale);
+}
+// the same from fixed-point sums: scale = 2^-32 / samples_per_pixel
+__global__ void tonemap_fixed_kernel(const AccumFx* __restrict__ accum, int32_t* __restrict__ rgb, int n_values, double scale) {
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n_values) rgb[i] = to_rgb_f64((double)accum[i] * scale);
+}
+// fixed-point sums -> float sums (one rounding per value); add = 1 accumulates into `out`
+__global__ void fixed_to_float_kernel(const AccumFx* __restrict__ accum, float* __restrict__ out, long long n_values, int add) {
+    long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n_values) return;
+    float v = (float)((double)accum[i] * (1.0 / 4294967296.0));
+    out[i] = add ? out[i] + v : v;
 }
 
 __global__ void intersect_kernel(DSceneView S, int mode, const float* __restrict__ rays, long long n, RtHit* __restrict__ out) {
@@ -125,6 +139,7 @@ int upload_scene(RtScene* s) {
     DMaterial* mats;
     DTexture* texs;
     DMedium* media;
+    DPrim* media_prims;
     float* pvec;
     unsigned short* pperm;
     int rc;
@@ -136,6 +151,7 @@ int upload_scene(RtScene* s) {
     if ((rc = upload(f.mats, &mats, s->owned, s->device_bytes))) return rc;
     if ((rc = upload(f.texs, &texs, s->owned, s->device_bytes))) return rc;
     if ((rc = upload(f.media, &media, s->owned, s->device_bytes))) return rc;
+    if ((rc = upload(f.media_prims, &media_prims, s->owned, s->device_bytes))) return rc;
     if ((rc = upload(f.perlin_vec, &pvec, s->owned, s->device_bytes))) return rc;
     if ((rc = upload(f.perlin_perm, &pperm, s->owned, s->device_bytes))) return rc;
     // image textures -> CUDA texture objects (RGBA8, point sampling, clamp, texel coordinates)
@@ -163,7 +179,7 @@ int upload_scene(RtScene* s) {
     }
     DImage* dimages;
     if ((rc = upload(images, &dimages, s->owned, s->device_bytes))) return rc;
-    v.nodes = nodes, v.nodes4 = f.nodes4.empty() ? nullptr : nodes4, v.n_nodes4 = (int)f.nodes4.size(), v.prims = prims, v.big = big, v.inst = inst, v.mats = mats, v.texs = texs, v.media = media;
+    v.nodes = nodes, v.nodes4 = f.nodes4.empty() ? nullptr : nodes4, v.n_nodes4 = (int)f.nodes4.size(), v.prims = prims, v.big = big, v.inst = inst, v.mats = mats, v.texs = texs, v.media = media, v.media_prims = media_prims;
     v.perlin_vec = pvec, v.perlin_perm = pperm, v.images = dimages;
     v.n_nodes = (int)f.nodes.size(), v.n_prims = (int)f.prims.size(), v.n_media = (int)f.media.size();
     v.n_perlin = (int)(f.perlin_vec.size() / (4 * RTB_PERLIN_POINTS));
@@ -180,13 +196,13 @@ void free_scene(RtScene* s) {
         for (auto t : s->textures) cudaDestroyTextureObject(t);
         for (size_t i = 0; i < s->arrays.size(); ++i) rtb::cache_free_array(s->arrays[i], s->array_extent[i].first, s->array_extent[i].second);
         for (auto& b : s->owned) rtb::cache_free(b.first, b.second);
-        rtb::cache_free(s->d_accum, s->scratch_values * sizeof(float));
+        rtb::cache_free(s->d_accum, s->scratch_values * sizeof(AccumFx));
+        rtb::cache_free(s->d_accum_f, s->scratch_values * sizeof(float));
         rtb::cache_free(s->d_rgb, s->scratch_values * sizeof(int32_t));
         rtb::cache_free(s->d_rays, sizeof(unsigned long long));
         if (s->ev0) cudaEventDestroy(s->ev0);
         if (s->ev1) cudaEventDestroy(s->ev1);
         free_wavefront(s);
-        free_warpfront(s);
         free_persist(s);
     }
     if (s->desc) rtb::free_desc(s->desc);
@@ -240,7 +256,7 @@ DRenderParams device_params(const RtParams* p, int first_sample, int spi, int ch
 }
 
 // the megakernel pipeline: samples [begin, begin+count) of every pixel, added into d_accum
-int launch_megakernel(const RtScene* s, const DCamera& cam, const RtParams* p, int begin, int count, float* d_accum, cudaStream_t stream,
+int launch_megakernel(const RtScene* s, const DCamera& cam, const RtParams* p, int begin, int count, AccumFx* d_accum, cudaStream_t stream,
                       RtProgressFn cb, void* user, int* launches) {
     int spi = p->samples_per_item > 0 ? p->samples_per_item : 16;
     spi = std::min(spi, count);
@@ -276,16 +292,84 @@ int pick_pipeline(const RtScene* s, const RtParams* p) {
     return persist_supports(s, p) ? RT_PIPELINE_PERSISTENT : RT_PIPELINE_MEGAKERNEL;  // measured fastest on C1-C4
 }
 
-int run_pipeline(RtScene* s, const DCamera& cam, const RtParams* p, int begin, int count, float* d_accum, cudaStream_t stream, RtProgressFn cb,
+int run_pipeline(RtScene* s, const DCamera& cam, const RtParams* p, int begin, int count, AccumFx* d_accum, cudaStream_t stream, RtProgressFn cb,
                  void* user, int* launches, int* used) {
     *used = pick_pipeline(s, p);
     if (*used == RT_PIPELINE_WAVEFRONT) return launch_wavefront(s, cam, p, begin, count, d_accum, stream, cb, user, launches);
-    if (*used == RT_PIPELINE_WAVEFRONT_SMEM) return launch_warpfront(s, cam, p, begin, count, d_accum, stream, cb, user, launches);
+    if (*used == RT_PIPELINE_WAVEFRONT_SMEM)
+        return set_error(RT_ERR_UNSUPPORTED, "RT_PIPELINE_WAVEFRONT_SMEM was a rejected experiment (tools/experiments/rt_warpfront.cu); the library no longer carries it");
     if (*used == RT_PIPELINE_PERSISTENT) return launch_persist(s, cam, p, begin, count, d_accum, stream, cb, user, launches);
     return launch_megakernel(s, cam, p, begin, count, d_accum, stream, cb, user, launches);
 }
 
 }  // namespace
+
+// samples [begin, begin + count) of every pixel ADDED into the fixed-point buffer d_accum (device memory of scene's device)
+int rtb::accumulate_fixed(const RtScene* scene, const RtCamera* cam, const RtParams* params, AccumFx* d_accum, cudaStream_t stream, RtProgressFn cb,
+                            void* user, RtStats* stats, bool sync_for_stats) {
+    int begin = params->sample_begin;
+    int count = params->sample_count > 0 ? params->sample_count : params->samples_per_pixel - begin;
+    if (count <= 0) return set_error(RT_ERR_INVALID, "render: empty sample range");
+    DCamera dc;
+    make_camera(*cam, dc);
+    int launches = 0;
+    if (stats) {
+        CU_TRY(cudaMemsetAsync(scene->d_rays, 0, sizeof(unsigned long long), stream));
+        CU_TRY(cudaEventRecord(scene->ev0, stream));
+    }
+    int used = 0;
+    int rc = run_pipeline(const_cast<RtScene*>(scene), dc, params, begin, count, d_accum, stream, cb, user, &launches, &used);
+    if (rc != RT_OK) return rc;
+    if (stats) {
+        std::memset(stats, 0, sizeof *stats);
+        stats->paths = (uint64_t)params->width * params->height * count;
+        stats->kernel_launches = launches;
+        stats->pipeline_used = used;
+        stats->bvh_layout_used = used == RT_PIPELINE_PERSISTENT ? persist_layout_used(scene, params) : 2;
+        if (sync_for_stats) {
+            CU_TRY(cudaEventRecord(scene->ev1, stream));
+            CU_TRY(cudaEventSynchronize(scene->ev1));
+            float ms = 0;
+            CU_TRY(cudaEventElapsedTime(&ms, scene->ev0, scene->ev1));
+            unsigned long long rays = 0;
+            CU_TRY(cudaMemcpy(&rays, scene->d_rays, sizeof rays, cudaMemcpyDeviceToHost));
+            stats->rays = rays;
+            stats->device_ms = ms;
+        }
+    }
+    return RT_OK;
+}
+
+static int ensure_scratch(RtScene* scene, size_t n_values) {
+    if (scene->scratch_values >= n_values) return RT_OK;
+    rtb::cache_free(scene->d_accum, scene->scratch_values * sizeof(AccumFx));
+    rtb::cache_free(scene->d_accum_f, scene->scratch_values * sizeof(float));
+    rtb::cache_free(scene->d_rgb, scene->scratch_values * sizeof(int32_t));
+    scene->d_accum = nullptr, scene->d_accum_f = nullptr, scene->d_rgb = nullptr, scene->scratch_values = 0;
+    CU_TRY(rtb::cache_malloc((void**)&scene->d_accum, n_values * sizeof(AccumFx)));
+    CU_TRY(rtb::cache_malloc((void**)&scene->d_accum_f, n_values * sizeof(float)));
+    CU_TRY(rtb::cache_malloc((void**)&scene->d_rgb, n_values * sizeof(int32_t)));
+    scene->scratch_values = n_values;
+    return RT_OK;
+}
+int rtb::scene_scratch(RtScene* scene, size_t n_values) { return ensure_scratch(scene, n_values); }
+
+static int tonemap_args(const void* a, const void* b, int32_t n_pixels, int32_t spp, int* device) {
+    if (!a || !b || n_pixels <= 0 || spp <= 0) return set_error(RT_ERR_INVALID, "rt_tonemap: bad argument");
+    int rc = have_device();
+    if (rc != RT_OK) return rc;
+    if (*device < 0) cudaGetDevice(device);
+    return RT_OK;
+}
+
+// Renderer::render's logger(j, H) is called once per row (raytrace.rs:182).  The pipelines report (samples done, samples
+// total); this adapter turns that into one call per row index, in increasing j, on the calling thread.
+void rtb::row_progress(int done, int total, void* user) {
+    rtb::RowProgress* r = (rtb::RowProgress*)user;
+    if (!r->cb) return;
+    int upto = total > 0 ? (int)((long long)r->rows * done / total) : r->rows;
+    while (r->reported < upto && r->reported < r->rows) r->cb(r->reported++, r->rows, r->user);
+}
 
 // ============================================================================ extern "C"
 
@@ -320,52 +404,76 @@ int rt_scene_info(const RtScene* scene, int32_t* n_prims, int32_t* n_bvh_nodes, 
     return RT_OK;
 }
 
-int rt_render_accumulate_device(const RtScene* scene, const RtCamera* cam, const RtParams* params, float* d_accum_rgb, void* stream_, RtStats* stats) {
+int rt_render_accumulate_fixed_device(const RtScene* scene, const RtCamera* cam, const RtParams* params, uint64_t* d_accum_fixed, void* stream_,
+                                      RtStats* stats) {
     int rc = validate_render(scene, cam, params);
     if (rc != RT_OK) return rc;
+    if (!d_accum_fixed) return set_error(RT_ERR_INVALID, "rt_render_accumulate_fixed_device: null accumulation buffer");
+    DeviceGuard g(scene->device);
+    return rtb::accumulate_fixed(scene, cam, params, (AccumFx*)d_accum_fixed, (cudaStream_t)stream_, nullptr, nullptr, stats, true);
+}
+
+int rt_render_accumulate_device(const RtScene* scene_, const RtCamera* cam, const RtParams* params, float* d_accum_rgb, void* stream_, RtStats* stats) {
+    int rc = validate_render(scene_, cam, params);
+    if (rc != RT_OK) return rc;
     if (!d_accum_rgb) return set_error(RT_ERR_INVALID, "rt_render_accumulate_device: null accumulation buffer");
+    RtScene* scene = const_cast<RtScene*>(scene_);
     cudaStream_t stream = (cudaStream_t)stream_;
     DeviceGuard g(scene->device);
-    int begin = params->sample_begin;
-    int count = params->sample_count > 0 ? params->sample_count : params->samples_per_pixel - begin;
-    if (count <= 0) return set_error(RT_ERR_INVALID, "render: empty sample range");
-    DCamera dc;
-    make_camera(*cam, dc);
-    int launches = 0;
-    if (stats) {
-        CU_TRY(cudaMemsetAsync(scene->d_rays, 0, sizeof(unsigned long long), stream));
-        CU_TRY(cudaEventRecord(scene->ev0, stream));
-    }
-    int used = 0;
-    rc = run_pipeline(const_cast<RtScene*>(scene), dc, params, begin, count, d_accum_rgb, stream, nullptr, nullptr, &launches, &used);
+    // the pipelines sum in fixed point (scene scratch); the caller's float buffer receives the converted sums
+    const size_t n_values = (size_t)3 * params->width * params->height;
+    if ((rc = ensure_scratch(scene, n_values)) != RT_OK) return rc;
+    CU_TRY(cudaMemsetAsync(scene->d_accum, 0, n_values * sizeof(AccumFx), stream));
+    rc = rtb::accumulate_fixed(scene, cam, params, scene->d_accum, stream, nullptr, nullptr, stats, false);
     if (rc != RT_OK) return rc;
+    fixed_to_float_kernel<<<(unsigned)((n_values + 255) / 256), 256, 0, stream>>>(scene->d_accum, d_accum_rgb, (long long)n_values, 1);
+    CU_TRY(cudaGetLastError());
     if (stats) {
+        stats->kernel_launches += 1;
         CU_TRY(cudaEventRecord(scene->ev1, stream));
         CU_TRY(cudaEventSynchronize(scene->ev1));
         float ms = 0;
         CU_TRY(cudaEventElapsedTime(&ms, scene->ev0, scene->ev1));
         unsigned long long rays = 0;
         CU_TRY(cudaMemcpy(&rays, scene->d_rays, sizeof rays, cudaMemcpyDeviceToHost));
-        stats->paths = (uint64_t)params->width * params->height * count;
-        stats->rays = rays;
-        stats->device_ms = ms;
-        stats->kernel_launches = launches;
-        stats->pipeline_used = used;
+        stats->rays = rays, stats->device_ms = ms;
     }
     return RT_OK;
 }
 
 int rt_tonemap_device(const float* d_accum_rgb, int32_t* d_rgb, int32_t n_pixels, int32_t samples_per_pixel, int device, void* stream_) {
-    if (!d_accum_rgb || !d_rgb || n_pixels <= 0 || samples_per_pixel <= 0) return set_error(RT_ERR_INVALID, "rt_tonemap_device: bad argument");
-    int rc = have_device();
+    int rc = tonemap_args(d_accum_rgb, d_rgb, n_pixels, samples_per_pixel, &device);
     if (rc != RT_OK) return rc;
-    if (device < 0) cudaGetDevice(&device);
     DeviceGuard g(device);
     int n = 3 * n_pixels;
     tonemap_kernel<<<(n + 255) / 256, 256, 0, (cudaStream_t)stream_>>>(d_accum_rgb, d_rgb, n, 1.0 / (double)samples_per_pixel);
     CU_TRY(cudaGetLastError());
     return RT_OK;
 }
+
+int rt_tonemap_fixed_device(const uint64_t* d_accum_fixed, int32_t* d_rgb, int32_t n_pixels, int32_t samples_per_pixel, int device, void* stream_) {
+    int rc = tonemap_args(d_accum_fixed, d_rgb, n_pixels, samples_per_pixel, &device);
+    if (rc != RT_OK) return rc;
+    DeviceGuard g(device);
+    int n = 3 * n_pixels;
+    tonemap_fixed_kernel<<<(n + 255) / 256, 256, 0, (cudaStream_t)stream_>>>((const AccumFx*)d_accum_fixed, d_rgb, n,
+                                                                             1.0 / (RT_ACCUM_FIXED_ONE * (double)samples_per_pixel));
+    CU_TRY(cudaGetLastError());
+    return RT_OK;
+}
+
+int rt_accum_fixed_to_float_device(const uint64_t* d_accum_fixed, float* d_accum_rgb, int64_t n_values, int device, void* stream_) {
+    if (!d_accum_fixed || !d_accum_rgb || n_values <= 0) return set_error(RT_ERR_INVALID, "rt_accum_fixed_to_float_device: bad argument");
+    int rc = have_device();
+    if (rc != RT_OK) return rc;
+    if (device < 0) cudaGetDevice(&device);
+    DeviceGuard g(device);
+    fixed_to_float_kernel<<<(unsigned)((n_values + 255) / 256), 256, 0, (cudaStream_t)stream_>>>((const AccumFx*)d_accum_fixed, d_accum_rgb, (long long)n_values, 0);
+    CU_TRY(cudaGetLastError());
+    return RT_OK;
+}
+
+void rt_release_cached_memory(void) { rtb::cache_release_all(); }
 
 int rt_render(const RtScene* scene_, const RtCamera* cam, const RtParams* params, float* accum_rgb, int32_t* rgb, RtProgressFn cb, void* user,
               RtStats* stats) {
@@ -374,44 +482,48 @@ int rt_render(const RtScene* scene_, const RtCamera* cam, const RtParams* params
     RtScene* scene = const_cast<RtScene*>(scene_);  // scratch buffers are cached in the scene object
     DeviceGuard g(scene->device);
     size_t n_values = (size_t)3 * params->width * params->height;
-    if (scene->scratch_values < n_values) {
-        rtb::cache_free(scene->d_accum, scene->scratch_values * sizeof(float));
-        rtb::cache_free(scene->d_rgb, scene->scratch_values * sizeof(int32_t));
-        scene->d_accum = nullptr, scene->d_rgb = nullptr, scene->scratch_values = 0;
-        CU_TRY(rtb::cache_malloc((void**)&scene->d_accum, n_values * sizeof(float)));
-        CU_TRY(rtb::cache_malloc((void**)&scene->d_rgb, n_values * sizeof(int32_t)));
-        scene->scratch_values = n_values;
-    }
-    int begin = params->sample_begin;
-    int count = params->sample_count > 0 ? params->sample_count : params->samples_per_pixel - begin;
-    if (count <= 0) return set_error(RT_ERR_INVALID, "render: empty sample range");
-    DCamera dc;
-    make_camera(*cam, dc);
+    if ((rc = ensure_scratch(scene, n_values)) != RT_OK) return rc;
     cudaStream_t stream = 0;
-    int launches = 0;
+    rtb::RowProgress rows{cb, user, params->height, 0};
+    RtStats local;
     CU_TRY(cudaMemsetAsync(scene->d_rays, 0, sizeof(unsigned long long), stream));
     CU_TRY(cudaEventRecord(scene->ev0, stream));
-    CU_TRY(cudaMemsetAsync(scene->d_accum, 0, n_values * sizeof(float), stream));
-    int used = 0;
-    rc = run_pipeline(scene, dc, params, begin, count, scene->d_accum, stream, cb, user, &launches, &used);
-    if (rc != RT_OK) return rc;
-    tonemap_kernel<<<(unsigned)((n_values + 255) / 256), 256, 0, stream>>>(scene->d_accum, scene->d_rgb, (int)n_values, 1.0 / (double)params->samples_per_pixel);
+    CU_TRY(cudaMemsetAsync(scene->d_accum, 0, n_values * sizeof(AccumFx), stream));
+    {
+        // stats are finalised below, after the tonemap: the timed region is render + tonemap
+        int begin = params->sample_begin;
+        int count = params->sample_count > 0 ? params->sample_count : params->samples_per_pixel - begin;
+        if (count <= 0) return set_error(RT_ERR_INVALID, "render: empty sample range");
+        DCamera dc;
+        make_camera(*cam, dc);
+        int launches = 0, used = 0;
+        rc = run_pipeline(scene, dc, params, begin, count, scene->d_accum, stream, cb ? rtb::row_progress : nullptr, &rows, &launches, &used);
+        if (rc != RT_OK) return rc;
+        std::memset(&local, 0, sizeof local);
+        local.paths = (uint64_t)params->width * params->height * count;
+        local.kernel_launches = launches, local.pipeline_used = used;
+        local.bvh_layout_used = used == RT_PIPELINE_PERSISTENT ? persist_layout_used(scene, params) : 2;
+    }
+    tonemap_fixed_kernel<<<(unsigned)((n_values + 255) / 256), 256, 0, stream>>>(scene->d_accum, scene->d_rgb, (int)n_values,
+                                                                                1.0 / (RT_ACCUM_FIXED_ONE * (double)params->samples_per_pixel));
     CU_TRY(cudaGetLastError());
-    launches += 1;
+    local.kernel_launches += 1;
     CU_TRY(cudaEventRecord(scene->ev1, stream));
-    if (accum_rgb) CU_TRY(cudaMemcpyAsync(accum_rgb, scene->d_accum, n_values * sizeof(float), cudaMemcpyDeviceToHost, stream));
+    if (accum_rgb) {
+        fixed_to_float_kernel<<<(unsigned)((n_values + 255) / 256), 256, 0, stream>>>(scene->d_accum, scene->d_accum_f, (long long)n_values, 0);
+        CU_TRY(cudaGetLastError());
+        CU_TRY(cudaMemcpyAsync(accum_rgb, scene->d_accum_f, n_values * sizeof(float), cudaMemcpyDeviceToHost, stream));
+    }
     if (rgb) CU_TRY(cudaMemcpyAsync(rgb, scene->d_rgb, n_values * sizeof(int32_t), cudaMemcpyDeviceToHost, stream));
     CU_TRY(cudaStreamSynchronize(stream));
+    rtb::row_progress(1, 1, &rows);  // whatever rows the pipeline's own reports did not cover
     if (stats) {
         float ms = 0;
         CU_TRY(cudaEventElapsedTime(&ms, scene->ev0, scene->ev1));
         unsigned long long rays = 0;
         CU_TRY(cudaMemcpy(&rays, scene->d_rays, sizeof rays, cudaMemcpyDeviceToHost));
-        stats->paths = (uint64_t)params->width * params->height * count;
-        stats->rays = rays;
-        stats->device_ms = ms;
-        stats->kernel_launches = launches;
-        stats->pipeline_used = used;
+        local.rays = rays, local.device_ms = ms;
+        *stats = local;
     }
     return RT_OK;
 }

@@ -166,11 +166,17 @@ RTB_DEV void philox4x32_10(uint32_t c0, uint32_t c1, uint32_t c2, uint32_t c3, u
 struct PathRng {
     uint32_t pixel, sample, draw, k0, k1;
 };
-RTB_DEV void rng_next4(PathRng& g, float u[4]) {
+#define RTB_PHILOX_TAG 0x52544232u
+// block `block` of draw g.draw: four uniforms.  Block 0 is what rng_next4 returns; further blocks serve the media
+// beyond the fourth (sample_media).
+RTB_DEV void rng_block(const PathRng& g, uint32_t block, float u[4]) {
     uint32_t r[4];
-    philox4x32_10(g.pixel, g.sample, g.draw, 0x52544232u, g.k0, g.k1, r);
-    g.draw += 1;
+    philox4x32_10(g.pixel, g.sample, g.draw, RTB_PHILOX_TAG + block, g.k0, g.k1, r);
     u[0] = u32_to_unit(r[0]), u[1] = u32_to_unit(r[1]), u[2] = u32_to_unit(r[2]), u[3] = u32_to_unit(r[3]);
+}
+RTB_DEV void rng_next4(PathRng& g, float u[4]) {
+    rng_block(g, 0u, u);
+    g.draw += 1;
 }
 
 // Uniform point inside the unit ball, drawn directly instead of by the rejection loop of
@@ -220,7 +226,9 @@ RTB_DEV PrimRec load_prim(const DPrim* p) {  // an element of the 32-byte-aligne
     const F8 v = ld8(p);
     return prim_from(v.lo, v.hi);
 }
-RTB_DEV PrimRec load_prim16(const DPrim* p) { return prim_from(ld4(p), ld4(reinterpret_cast<const char*>(p) + 16)); }  // 16-byte aligned only
+// two 128-bit loads: records that are only 16-byte aligned (DMedium.boundary), and the out-of-line compound-boundary
+// loop, where ptxas 12.9 crashes on the 256-bit form
+RTB_DEV PrimRec load_prim16(const DPrim* p) { return prim_from(ld4(p), ld4(reinterpret_cast<const char*>(p) + 16)); }
 RTB_DEV int prim_instance(const PrimRec& p) { return (int)((p.meta >> PRIM_INST_SHIFT) & PRIM_INST_MASK); }
 
 // Sphere::hit (shapes.rs:57-82).  `from_surface`: the ray starts on this very sphere, so one root is
@@ -560,35 +568,69 @@ RTB_DEV void closest_hit_linear(const DSceneView& S, const Ray& r, float tmin, f
 }
 
 // ------------------------------------------------------------------ media (volumes.rs:25-65)
-// deterministic part: the boundary interval clipped to [tmin, tmax]
-RTB_DEV bool medium_interval(const DSceneView& S, const PrimRec& b, const Ray& r, float tmin, float tmax, float& t1, float& t2) {
-    float te, tx;
-    if ((b.meta & PRIM_KIND_MASK) == PRIM_SPHERE) {
-        if (!sphere_interval(S, b, r, te, tx)) return false;
-    } else {
-        Ray ro = to_object_space(S, prim_instance(b), r);
-        int fe, fx;
-        if (!box_slabs(b, ro, -1, te, tx, fe, fx)) return false;
+// both crossings of one boundary primitive over (-inf, +inf), t0 <= t1 (a rect has one: t0 == t1)
+RTB_DEV bool boundary_crossings(const DSceneView& S, const PrimRec& b, const Ray& r, float& t0, float& t1) {
+    if ((b.meta & PRIM_KIND_MASK) == PRIM_SPHERE) return sphere_interval(S, b, r, t0, t1);
+    Ray ro = to_object_space(S, prim_instance(b), r);
+    int fe, fx;
+    return box_slabs(b, ro, -1, t0, t1, fe, fx);
+}
+// A boundary made of several primitives (ConstantMedium<O: Hittable>, volumes.rs:7-11): h1 = the closest hit of the
+// whole boundary over (-inf, inf), h2 = its closest hit from h1.t + 0.001 on (volumes.rs:27-34).  Every primitive
+// answers a range query with its first crossing inside the range, the list with the smallest of those.
+RTB_DEV_NOINLINE V3 compound_boundary(const DSceneView& S, int first, int count, float ox, float oy, float oz, float dx, float dy, float dz) {
+    Ray r;
+    r.o = v3(ox, oy, oz), r.d = v3(dx, dy, dz);
+    float h1 = RTB_INF, h2 = RTB_INF;
+    for (int i = first; i < first + count; ++i) {
+        float t0, t1;
+        if (boundary_crossings(S, load_prim16(S.media_prims + i), r, t0, t1)) h1 = fminf(h1, t0);
     }
-    if (!(tx >= te + 0.001f)) return false;  // second boundary.hit(h1.t + 0.001, inf) finds nothing
+    if (h1 < RTB_INF) {
+        const float from = h1 + 0.001f;
+        for (int i = first; i < first + count; ++i) {
+            float t0, t1;
+            if (!boundary_crossings(S, load_prim16(S.media_prims + i), r, t0, t1)) continue;
+            const float t = t0 >= from ? t0 : t1;
+            if (t >= from) h2 = fminf(h2, t);
+        }
+    }
+    return v3(h1, h2, 0.f);
+}
+
+// deterministic part: the boundary interval clipped to [tmin, tmax]
+RTB_DEV bool medium_interval(const DSceneView& S, const PrimRec& b, int first, int count, const Ray& r, float tmin, float tmax, float& t1, float& t2) {
+    float te, tx;
+    if (count > 1) {
+        const V3 h = compound_boundary(S, first, count, r.o.x, r.o.y, r.o.z, r.d.x, r.d.y, r.d.z);
+        te = h.x, tx = h.y;
+        if (!(tx < RTB_INF)) return false;
+    } else {
+        if (!boundary_crossings(S, b, r, te, tx)) return false;
+        if (!(tx >= te + 0.001f)) return false;  // second boundary.hit(h1.t + 0.001, inf) finds nothing
+    }
     t1 = fmaxf(te, tmin), t2 = fminf(tx, tmax);
     if (t1 >= t2) return false;
     t1 = fmaxf(t1, 0.0f);
     return true;
 }
 
-// free-flight sampling in every medium; keeps the closest event.  u[m] is the uniform of medium m.
-RTB_DEV void sample_media(const DSceneView& S, const Ray& r, float tmin, const float* u, float& t_best, int& medium_best) {
+// free-flight sampling in every medium; keeps the closest event.  Medium m uses uniform m & 3 of Philox block
+// (pixel, sample, draw, tag + (m >> 2)): scenes with up to four media draw exactly one block per segment.
+RTB_DEV void sample_media(const DSceneView& S, const Ray& r, float tmin, const PathRng& rng, float& t_best, int& medium_best) {
     medium_best = -1;
     float len = sqrtf(dot(r.d, r.d));
+    float u[4];
     for (int m = 0; m < S.n_media; ++m) {
+        if ((m & 3) == 0) rng_block(rng, (uint32_t)(m >> 2), u);
         const DMedium* M = S.media + m;
         PrimRec b = load_prim16(&M->boundary);
-        float4 tail = ld4(reinterpret_cast<const char*>(M) + 32);
+        float4 tail = ld4(reinterpret_cast<const char*>(M) + 32);  // neg_inv_density, mat, first, count
         float t1, t2;
-        if (!medium_interval(S, b, r, tmin, t_best, t1, t2)) continue;
+        if (!medium_interval(S, b, (int)as_uint(tail.z), (int)as_uint(tail.w), r, tmin, t_best, t1, t2)) continue;
         float inside = (t2 - t1) * len;
-        float dist = tail.x * fast_log(u[m]);  // neg_inv_density * ln(U)
+        float um = (m & 3) == 0 ? u[0] : ((m & 3) == 1 ? u[1] : ((m & 3) == 2 ? u[2] : u[3]));
+        float dist = tail.x * fast_log(um);  // neg_inv_density * ln(U)
         if (dist > inside) continue;
         t_best = t1 + dist / len;
         medium_best = m;
@@ -681,20 +723,14 @@ RTB_DEV V3 texture_leaf(const DSceneView& S, int tex, float u, float v, V3 p, No
 }
 
 RTB_DEV V3 texture_value(const DSceneView& S, int tex, float u, float v, V3 p, NoiseReq* req = nullptr) {
-    const DTexture& T = S.texs[tex];
-    if (T.kind == TEX_CHECKER) {  // textures.rs:40-49
-        float sines = sinf(5.0f * p.x) * sinf(5.0f * p.y) * sinf(5.0f * p.z);
-        return texture_leaf(S, sines < 0.0f ? T.a : T.b, u, v, p, req);
+    if (S.texs[tex].kind == TEX_CHECKER) {  // textures.rs:40-49; nested checkers see the same p, hence the same side
+        const float sines = sinf(5.0f * p.x) * sinf(5.0f * p.y) * sinf(5.0f * p.z);
+        for (int level = 0; level < RTB_CHECKER_DEPTH && S.texs[tex].kind == TEX_CHECKER; ++level) tex = sines < 0.0f ? S.texs[tex].a : S.texs[tex].b;
     }
     return texture_leaf(S, tex, u, v, p, req);
 }
 
-RTB_DEV bool texture_needs_uv(const DSceneView& S, int tex) {
-    const DTexture& T = S.texs[tex];
-    if (T.kind == TEX_IMAGE) return true;
-    if (T.kind == TEX_CHECKER) return S.texs[T.a].kind == TEX_IMAGE || S.texs[T.b].kind == TEX_IMAGE;
-    return false;
-}
+RTB_DEV bool texture_needs_uv(const DSceneView& S, int tex) { return S.texs[tex].needs_uv != 0; }
 
 // ------------------------------------------------------------------ hit attributes (hittable.rs:18-30 + transforms)
 struct Surface {
@@ -857,9 +893,7 @@ RTB_DEV bool extend_and_shade(const DSceneView& S, PathState& ps, PathRng& rng, 
     int medium = -1;
     rng.draw = 1u + 2u * (uint32_t)segment;
     if (S.n_media > 0) {
-        float um[4];
-        rng_next4(rng, um);
-        sample_media(S, ps.ray, RTB_T_MIN, um, t, medium);
+        sample_media(S, ps.ray, RTB_T_MIN, rng, t, medium);
     }
     int prim, face;
     closest_hit(S, ps.ray, RTB_T_MIN, t, ps.origin_prim, ps.origin_face, t, prim, face);
@@ -882,6 +916,14 @@ RTB_DEV bool extend_and_shade(const DSceneView& S, PathState& ps, PathRng& rng, 
     return alive;
 }
 
+// ------------------------------------------------------------------ accumulation in fixed point (AccumFx, rt_types.h)
+// One radiance sample -> 2^-32 units, rounded to nearest.  Samples are >= 0 (albedos, emission and noise values are);
+// NaN counts as 0 and a sample is capped at 2^20 so that a 64-bit sum holds 2^11 such extremes (2^31 ordinary ones).
+RTB_DEV AccumFx radiance_fixed(float x) {
+    x = x == x ? fminf(fmaxf(x, 0.0f), 1048576.0f) : 0.0f;
+    return (AccumFx)fmaf(x, 4294967296.0f, 0.5f);
+}
+
 // ------------------------------------------------------------------ one work item = one pixel x a run of samples
 // item -> (tile, lane): a warp covers an 8x4 pixel tile so that its 32 camera rays start coherent.
 RTB_DEV bool item_to_pixel(const DRenderParams& P, long long item, int& px, int& py, int& chunk) {
@@ -897,7 +939,7 @@ RTB_DEV bool item_to_pixel(const DRenderParams& P, long long item, int& px, int&
 // render_pixel's sample loop (raytrace.rs:188-198) for samples [first, first + count) of one pixel.
 // Paths are regenerated in place: every loop iteration advances whatever path the thread currently holds by
 // one segment, so the lanes of a warp stay busy until their whole run of samples is finished.
-RTB_DEV void integrate_item(const DSceneView& S, const DCamera& cam, const DRenderParams& P, int px, int py, int first, int count, float sum[3],
+RTB_DEV void integrate_item(const DSceneView& S, const DCamera& cam, const DRenderParams& P, int px, int py, int first, int count, AccumFx sum[3],
                             uint32_t& n_rays) {
     PathRng rng;
     rng.pixel = (uint32_t)(py * P.width + px);
@@ -907,7 +949,7 @@ RTB_DEV void integrate_item(const DSceneView& S, const DCamera& cam, const DRend
     ps.depth = 0, ps.origin_prim = -1, ps.origin_face = 0;
     ps.beta = v3(0.f, 0.f, 0.f);
     ps.ray.o = ps.ray.d = v3(0.f, 0.f, 0.f);
-    V3 acc = v3(0.f, 0.f, 0.f);
+    AccumFx acc[3] = {0ull, 0ull, 0ull};
     bool alive = false;
     int next = 0;
     for (;;) {
@@ -926,9 +968,9 @@ RTB_DEV void integrate_item(const DSceneView& S, const DCamera& cam, const DRend
         V3 radiance;
         n_rays += ps.depth > 0 ? 1u : 0u;
         alive = extend_and_shade(S, ps, rng, P.max_depth - ps.depth, radiance);
-        if (!alive) acc = acc + radiance;
+        if (!alive) acc[0] += radiance_fixed(radiance.x), acc[1] += radiance_fixed(radiance.y), acc[2] += radiance_fixed(radiance.z);
     }
-    sum[0] = acc.x, sum[1] = acc.y, sum[2] = acc.z;
+    sum[0] = acc[0], sum[1] = acc[1], sum[2] = acc[2];
 }
 
 // ------------------------------------------------------------------ wavefront path state (rt_wavefront.cu)
@@ -962,9 +1004,7 @@ RTB_DEV void wf_presample_media(const DSceneView& S, const DRenderParams& P, WfS
         r.o = v3(s.A.x, s.A.y, s.A.z), r.d = v3(s.B.x, s.B.y, s.B.z);
         PathRng rng;
         rng.pixel = as_uint(s.A.w), rng.sample = as_uint(s.C.w), rng.draw = 1u + 2u * (uint32_t)segment, rng.k0 = P.seed_lo, rng.k1 = P.seed_hi;
-        float um[4];
-        rng_next4(rng, um);
-        sample_media(S, r, RTB_T_MIN, um, t, medium);
+        sample_media(S, r, RTB_T_MIN, rng, t, medium);
     }
     s.D.x = t;
     s.D.y = as_float(medium >= 0 ? (uint32_t)(WF_MEDIUM | medium) : 0xFFFFFFFFu);
@@ -1077,7 +1117,7 @@ RTB_DEV void intersect_query(const DSceneView& S, int mode, const float* q, RtHi
     if (mode == QUERY_MEDIUM) {
         PrimRec b = load_prim16(&S.media[0].boundary);
         float t1, t2;
-        if (medium_interval(S, b, r, tmin, tmax, t1, t2)) out.t = t1, out.u = t2, out.material = S.media[0].mat;
+        if (medium_interval(S, b, S.media[0].first, S.media[0].count, r, tmin, tmax, t1, t2)) out.t = t1, out.u = t2, out.material = S.media[0].mat;
         return;
     }
     float t;

@@ -2,10 +2,11 @@
 //
 // The reference parallelises Renderer::render over image rows with rayon on one host (src/raytrace.rs:176-185).
 // Here every (pixel, sample) path is independent and owns a Philox counter, so device g of G renders ALL pixels
-// for the g-th contiguous slice of the sample range; the G float accumulation buffers are summed onto the root
-// device with ONE ncclReduce over NVLink and the root tonemaps (to_rgb, raytrace.rs:59-68).  No other exchange
-// exists on this path.  (Under torch.distributed — one process per GPU — the same slicing is done by
-// mu_lambda_raytracer_b200/distributed.py with rt_render_accumulate_device + dist.reduce.)
+// for the g-th contiguous slice of the sample range; the G fixed-point accumulation buffers (64-bit integers, so the sum
+// is exact and the image identical to the one-GPU render) are summed onto the root device with ONE ncclReduce over
+// NVLink and the root tonemaps (to_rgb, raytrace.rs:59-68).  No other exchange exists on this path.  (Under
+// torch.distributed — one process per GPU — the same slicing is done by mu_lambda_raytracer_b200/distributed.py with
+// rt_render_accumulate_fixed_device + dist.reduce.)
 //
 // NCCL is bound at run time (dlopen of libnccl.so.2): the library has no link-time dependency on it, and inside a
 // process that already loaded a libnccl (PyTorch) the same copy is reused.
@@ -26,7 +27,7 @@ namespace {
 // the handful of NCCL entry points used, declared locally so that no nccl.h is needed at build time
 typedef struct ncclComm* ncclComm_t;
 typedef int ncclResult_t;  // 0 = ncclSuccess
-enum { kNcclFloat = 7, kNcclSum = 0 };
+enum { kNcclUint64 = 5, kNcclFloat = 7, kNcclSum = 0 };  // ncclDataType_t / ncclRedOp_t values of nccl.h
 
 struct Nccl {
     void* so = nullptr;
@@ -152,16 +153,8 @@ int rt_render_multi(RtScene* const* scenes, int32_t n_scenes, const RtCamera* ca
     const size_t n_values = (size_t)3 * params->width * params->height;
     // per-device accumulation buffers (the scene's scratch, grown on demand)
     for (int g = 0; g < n_scenes; ++g) {
-        RtScene* s = scenes[g];
-        rtb::DeviceGuard guard(s->device);
-        if (s->scratch_values < n_values) {
-            rtb::cache_free(s->d_accum, s->scratch_values * sizeof(float));
-            rtb::cache_free(s->d_rgb, s->scratch_values * sizeof(int32_t));
-            s->d_accum = nullptr, s->d_rgb = nullptr, s->scratch_values = 0;
-            CU_TRY(rtb::cache_malloc((void**)&s->d_accum, n_values * sizeof(float)));
-            CU_TRY(rtb::cache_malloc((void**)&s->d_rgb, n_values * sizeof(int32_t)));
-            s->scratch_values = n_values;
-        }
+        rtb::DeviceGuard guard(scenes[g]->device);
+        if ((rc = rtb::scene_scratch(scenes[g], n_values)) != RT_OK) return rc;
     }
     RtScene* root = scenes[0];
     struct Events {  // destroyed on every exit
@@ -179,39 +172,40 @@ int rt_render_multi(RtScene* const* scenes, int32_t n_scenes, const RtCamera* ca
         CU_TRY(cudaEventCreate(&t1));
         CU_TRY(cudaEventRecord(t0, 0));
     }
-    // one host thread per device: zero, render the slice (the wavefront driver polls its counters, so it blocks)
+    // one host thread per device: zero, render the slice.  The root's slice runs on the calling thread, which is the
+    // only one allowed to invoke the logger: its progress paces the per-row reports (every device has the same work).
     std::vector<int> codes(n_scenes, RT_OK);
     std::vector<std::string> messages(n_scenes);
     std::vector<RtStats> part(n_scenes);
     std::vector<std::thread> threads;
-    for (int g = 0; g < n_scenes; ++g) {
-        threads.emplace_back([&, g] {
-            RtScene* s = scenes[g];
-            cudaSetDevice(s->device);
-            RtParams p = *params;
-            rt_sample_slice(begin, count, n_scenes, g, &p.sample_begin, &p.sample_count);
-            std::memset(&part[g], 0, sizeof(RtStats));
-            cudaError_t e = cudaMemsetAsync(s->d_accum, 0, n_values * sizeof(float), 0);
-            if (e != cudaSuccess) {
-                codes[g] = RT_ERR_CUDA, messages[g] = cudaGetErrorString(e);
-                return;
-            }
-            if (p.sample_count > 0) {
-                codes[g] = rt_render_accumulate_device(s, cam, &p, s->d_accum, nullptr, &part[g]);
-                if (codes[g] != RT_OK) messages[g] = rt_last_error();
-            }
-        });
-    }
+    rtb::RowProgress rows{cb, user, params->height, 0};
+    auto render_slice = [&](int g) {
+        RtScene* s = scenes[g];
+        cudaSetDevice(s->device);
+        RtParams p = *params;
+        rt_sample_slice(begin, count, n_scenes, g, &p.sample_begin, &p.sample_count);
+        std::memset(&part[g], 0, sizeof(RtStats));
+        cudaError_t e = cudaMemsetAsync(s->d_accum, 0, n_values * sizeof(rtb::AccumFx), 0);
+        if (e != cudaSuccess) {
+            codes[g] = RT_ERR_CUDA, messages[g] = cudaGetErrorString(e);
+            return;
+        }
+        if (p.sample_count > 0) {
+            codes[g] = rtb::accumulate_fixed(s, cam, &p, s->d_accum, 0, (g == 0 && cb) ? rtb::row_progress : nullptr, &rows, &part[g], true);
+            if (codes[g] != RT_OK) messages[g] = rt_last_error();
+        }
+    };
+    for (int g = 1; g < n_scenes; ++g) threads.emplace_back(render_slice, g);
+    render_slice(0);
     for (auto& t : threads) t.join();
     for (int g = 0; g < n_scenes; ++g)
         if (codes[g] != RT_OK) return rtb::set_error(codes[g], "device %d: %s", devices[g], messages[g].c_str());
-    if (cb) cb(count, count, user);
     // the one exchange step of the path: sum the accumulation buffers onto the root
     Nccl& n = nccl();
     ncclResult_t r = n.GroupStart();
     for (int g = 0; g < n_scenes && r == 0; ++g) {
         cudaSetDevice(devices[g]);
-        r = n.Reduce(scenes[g]->d_accum, scenes[g]->d_accum, n_values, kNcclFloat, kNcclSum, 0, comms[g], 0);
+        r = n.Reduce(scenes[g]->d_accum, scenes[g]->d_accum, n_values, kNcclUint64, kNcclSum, 0, comms[g], 0);
     }
     ncclResult_t r2 = n.GroupEnd();
     if (r == 0) r = r2;
@@ -221,12 +215,16 @@ int rt_render_multi(RtScene* const* scenes, int32_t n_scenes, const RtCamera* ca
         CU_TRY(cudaStreamSynchronize(0));
     }
     rtb::DeviceGuard guard(root->device);
-    rc = rt_tonemap_device(root->d_accum, root->d_rgb, params->width * params->height, params->samples_per_pixel, root->device, nullptr);
+    rc = rt_tonemap_fixed_device((const uint64_t*)root->d_accum, root->d_rgb, params->width * params->height, params->samples_per_pixel, root->device, nullptr);
     if (rc != RT_OK) return rc;
     CU_TRY(cudaEventRecord(t1, 0));
-    if (accum_rgb) CU_TRY(cudaMemcpyAsync(accum_rgb, root->d_accum, n_values * sizeof(float), cudaMemcpyDeviceToHost, 0));
+    if (accum_rgb) {
+        if ((rc = rt_accum_fixed_to_float_device((const uint64_t*)root->d_accum, root->d_accum_f, (int64_t)n_values, root->device, nullptr)) != RT_OK) return rc;
+        CU_TRY(cudaMemcpyAsync(accum_rgb, root->d_accum_f, n_values * sizeof(float), cudaMemcpyDeviceToHost, 0));
+    }
     if (rgb) CU_TRY(cudaMemcpyAsync(rgb, root->d_rgb, n_values * sizeof(int32_t), cudaMemcpyDeviceToHost, 0));
     CU_TRY(cudaStreamSynchronize(0));
+    rtb::row_progress(1, 1, &rows);  // the rows the root's own progress reports did not cover
     if (stats) {
         float ms = 0;
         CU_TRY(cudaEventElapsedTime(&ms, t0, t1));
@@ -234,7 +232,7 @@ int rt_render_multi(RtScene* const* scenes, int32_t n_scenes, const RtCamera* ca
         for (int g = 0; g < n_scenes; ++g) stats->paths += part[g].paths, stats->rays += part[g].rays, stats->kernel_launches += part[g].kernel_launches;
         stats->kernel_launches += 1;
         stats->device_ms = ms;  // root-device events around render + reduce + tonemap (every other device finishes before the reduce does)
-        stats->pipeline_used = part[0].pipeline_used;
+        stats->pipeline_used = part[0].pipeline_used, stats->bvh_layout_used = part[0].bvh_layout_used;
     }
     return RT_OK;
 }

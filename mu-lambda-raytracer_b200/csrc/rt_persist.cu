@@ -140,7 +140,7 @@ enum { PSS_SHADE_PHASES, PSS_SHADE_ACT, PSS_SHADE_DONE, PSS_SHADE_ONPARK, PSS_EX
 #define PS_SCENE_PRIMS 2
 template <bool STATS, bool WIDE, int SD, int NT, int SCENE>
 __global__ void __launch_bounds__(NT, (STATS || NT > 128) ? 1 : PS_MIN_BLOCKS) persist_kernel(DSceneView S, DCamera cam, DRenderParams P, PsCounters* __restrict__ ctr,
-                                                             float* __restrict__ accum, unsigned long long* __restrict__ rays_out,
+                                                             AccumFx* __restrict__ accum, unsigned long long* __restrict__ rays_out,
                                                              unsigned int chunk_size, unsigned long long* __restrict__ stats, PsTune tune) {
     unsigned int st_[PSS_COUNT];
     if (STATS)
@@ -273,10 +273,10 @@ __global__ void __launch_bounds__(NT, (STATS || NT > 128) ? 1 : PS_MIN_BLOCKS) p
                 }
             }
             if (shade && !alive) {  // the path ended: beta * (emission | background | 0) -> its pixel
-                float* dst = accum + 3 * (size_t)pixel_out;
-                if (radiance.x != 0.f) atomicAdd(dst + 0, radiance.x);
-                if (radiance.y != 0.f) atomicAdd(dst + 1, radiance.y);
-                if (radiance.z != 0.f) atomicAdd(dst + 2, radiance.z);
+                AccumFx* dst = accum + 3 * (size_t)pixel_out;  // 64-bit integer REDs: order-independent sums
+                if (radiance.x != 0.f) atomicAdd(dst + 0, radiance_fixed(radiance.x));
+                if (radiance.y != 0.f) atomicAdd(dst + 1, radiance_fixed(radiance.y));
+                if (radiance.z != 0.f) atomicAdd(dst + 2, radiance_fixed(radiance.z));
             }
             // regenerate: the next camera paths of the job, handed out in reservation order
             bool need = act && !alive;
@@ -450,7 +450,7 @@ bool persist_supports(const RtScene* s, const RtParams* p) { return p->max_depth
 
 namespace {
 
-typedef void (*PersistFn)(DSceneView, DCamera, DRenderParams, PsCounters*, float*, unsigned long long*, unsigned int, unsigned long long*, PsTune);
+typedef void (*PersistFn)(DSceneView, DCamera, DRenderParams, PsCounters*, AccumFx*, unsigned long long*, unsigned int, unsigned long long*, PsTune);
 struct Variant {
     int layout, smem_stack, threads, scene;
     PersistFn fn, fn_stats;
@@ -501,7 +501,7 @@ int pick_variant(const RtScene* s, const RtParams* p) {
 
 int persist_layout_used(const RtScene* s, const RtParams* p) { return kVariants[pick_variant(s, p)].layout; }
 
-int launch_persist(RtScene* s, const DCamera& cam, const RtParams* p, int begin, int count, float* d_accum, cudaStream_t stream, RtProgressFn cb,
+int launch_persist(RtScene* s, const DCamera& cam, const RtParams* p, int begin, int count, AccumFx* d_accum, cudaStream_t stream, RtProgressFn cb,
                    void* user, int* launches) {
     if (!persist_supports(s, p)) return set_error(RT_ERR_UNSUPPORTED, "persistent pipeline: max_depth above %d or more than 2^24 primitives", WF_DEPTH_MASK);
     if (p->bvh_layout != 0 && p->bvh_layout != 2 && p->bvh_layout != 4) return set_error(RT_ERR_INVALID, "render: bvh_layout must be 0 (auto), 2 or 4");

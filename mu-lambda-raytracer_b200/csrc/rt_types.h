@@ -92,17 +92,26 @@ struct alignas(16) DTexture {
     int32_t a, b;  // CHECKER: odd/even texture; NOISE: perlin table; IMAGE: image
     float scale;
     float color[3];
-    int32_t pad;
+    int32_t needs_uv;  // an image texture is reachable from here (through checkers)
 };
+#define RTB_CHECKER_DEPTH 8
 
-// ---- constant-density medium (volumes.rs:7-65): boundary primitive + isotropic phase material
+// ---- constant-density medium (volumes.rs:7-65): boundary + isotropic phase material.  The boundary is any Hittable in
+// the reference: media_prims[first .. first + count) are its surface primitives; `boundary` repeats the first one so
+// that the usual single-primitive boundary costs no extra fetch.
 struct alignas(16) DMedium {
     DPrim boundary;
     float neg_inv_density;
     int32_t mat;
-    int32_t desc_node;
-    int32_t pad;
+    int32_t first;
+    int32_t count;
 };
+
+// ---- accumulation: radiance sums are 64-bit FIXED-POINT integers (32 fractional bits, RT_ACCUM_FIXED_ONE of the ABI).
+// Integer addition is associative, so the sums — and with them the image — do not depend on the order in which the
+// device's reductions land, nor on how the samples are split over launches or GPUs: one seed gives one image, bit for
+// bit, as the reference's per-row PCG streams do (src/raytrace.rs:179,197).
+typedef unsigned long long AccumFx;
 
 struct DCamera {  // camera.rs:3-12, computed on the host in f64 by Camera::new's formulas
     float origin[3];
@@ -115,7 +124,7 @@ struct DCamera {  // camera.rs:3-12, computed on the host in f64 by Camera::new'
 };
 
 #define RTB_PERLIN_POINTS 1024
-#define RTB_MAX_MEDIA 4
+#define RTB_MAX_MEDIA 4096  // free-flight uniforms come four per Philox block (rt_device.cuh: sample_media)
 #define RTB_BVH_STACK 48
 #define RTB_WIDE_STACK 64   // 4-byte keys of the 4-wide traversal (flatten.cpp falls back to the binary tree beyond it)
 #define RTB_BIG_SPHERE_RADIUS 100.0
@@ -135,6 +144,7 @@ struct DSceneView {
     const DMaterial* mats;
     const DTexture* texs;
     const DMedium* media;
+    const DPrim* media_prims;  // boundary primitives of all media
     const float* perlin_vec;          // n_perlin x 1024 x 4 floats (xyz, pad)
     const unsigned short* perlin_perm;  // n_perlin x 3 x 1024
     const DImage* images;

@@ -36,7 +36,7 @@ struct WfCounters {
 struct WfJob {
     DCamera cam;
     DRenderParams P;
-    float* accum;
+    AccumFx* accum;
 };
 
 struct WfView {
@@ -71,7 +71,7 @@ __device__ __forceinline__ float4 ld_stream(const float4* p) { return __ldcs(p);
 __device__ __forceinline__ void st_stream(float4* p, float4 v) { __stcs(p, v); }
 
 // ---------------------------------------------------------------------------------------------------------------
-__global__ void wf_reset_kernel(WfView W, unsigned int n_init, unsigned long long total, DCamera cam, DRenderParams P, float* accum) {
+__global__ void wf_reset_kernel(WfView W, unsigned int n_init, unsigned long long total, DCamera cam, DRenderParams P, AccumFx* accum) {
     W.job->cam = cam, W.job->P = P, W.job->accum = accum;
     WfCounters* c = W.ctr;
     c->q_count[0] = n_init, c->q_count[1] = 0, c->q_head = 0;
@@ -288,7 +288,7 @@ __global__ void __launch_bounds__(WF_SHADE_THREADS, 3) wf_shade_kernel(DSceneVie
     __shared__ unsigned int queue_base;
     WfCounters* ctr = W.ctr;
     const DRenderParams P = W.job->P;
-    float* __restrict__ accum = W.job->accum;
+    AccumFx* __restrict__ accum = W.job->accum;
     int cls = -1;
     unsigned int item = 0, n_in_class = 0;
     {
@@ -327,10 +327,10 @@ __global__ void __launch_bounds__(WF_SHADE_THREADS, 3) wf_shade_kernel(DSceneVie
             __syncthreads();
             if (dead) {
                 unsigned int pixel = __float_as_uint(s.A.w);
-                float* dst = accum + 3 * (size_t)pixel;
-                if (radiance.x != 0.f) atomicAdd(dst + 0, radiance.x);
-                if (radiance.y != 0.f) atomicAdd(dst + 1, radiance.y);
-                if (radiance.z != 0.f) atomicAdd(dst + 2, radiance.z);
+                AccumFx* dst = accum + 3 * (size_t)pixel;
+                if (radiance.x != 0.f) atomicAdd(dst + 0, radiance_fixed(radiance.x));
+                if (radiance.y != 0.f) atomicAdd(dst + 1, radiance_fixed(radiance.y));
+                if (radiance.z != 0.f) atomicAdd(dst + 2, radiance_fixed(radiance.z));
                 unsigned long long path = path_base + dead_rank;
                 if (path < ctr->total_paths) {
                     wf_init_path(S, W.job->cam, P, path, s);
@@ -415,7 +415,7 @@ void free_wavefront(RtScene* s) {
     s->wf = nullptr;
 }
 
-int launch_wavefront(RtScene* s, const DCamera& cam, const RtParams* p, int begin, int count, float* d_accum, cudaStream_t stream, RtProgressFn cb,
+int launch_wavefront(RtScene* s, const DCamera& cam, const RtParams* p, int begin, int count, AccumFx* d_accum, cudaStream_t stream, RtProgressFn cb,
                      void* user, int* launches) {
     if (p->max_depth > WF_DEPTH_MASK) return set_error(RT_ERR_UNSUPPORTED, "wavefront pipeline: max_depth above %d", WF_DEPTH_MASK);
     if (p->max_depth <= 0) return RT_OK;  // every path returns Color::ZERO at once (raytrace.rs:87-89)

@@ -32,10 +32,17 @@ struct DeviceGuard {  // run on the scene's device, restore the caller's afterwa
 };
 
 struct WavefrontState;  // rt_wavefront.cu
-struct WarpfrontState;  // rt_warpfront.cu
 struct PersistState;    // rt_persist.cu
 
 DRenderParams device_params(const RtParams* p, int first_sample, int spi, int chunks);
+int persist_layout_used(const RtScene* s, const RtParams* p);
+
+struct RowProgress {  // see rtb::row_progress (rt_api.cu)
+    RtProgressFn cb;
+    void* user;
+    int rows, reported;
+};
+void row_progress(int done, int total, void* user);
 
 }  // namespace rtb
 
@@ -50,28 +57,28 @@ struct RtScene {
     int64_t device_bytes = 0;
     rtb::OwnedDesc* desc = nullptr;  // deep copy of the description (sub-tree queries of rt_intersect_batch)
     // scratch of rt_render (host-buffer entry point), grown on demand
-    float* d_accum = nullptr;
+    rtb::AccumFx* d_accum = nullptr;  // fixed-point radiance sums (rt_types.h)
+    float* d_accum_f = nullptr;       // the same as floats, for callers that ask for them
     int32_t* d_rgb = nullptr;
     size_t scratch_values = 0;
     unsigned long long* d_rays = nullptr;
     cudaEvent_t ev0 = nullptr, ev1 = nullptr;
     rtb::WavefrontState* wf = nullptr;  // global path pool + queues (RT_PIPELINE_WAVEFRONT), allocated on first use
     rtb::PersistState* ps = nullptr;    // counters of the persistent pipeline (RT_PIPELINE_PERSISTENT)
-    rtb::WarpfrontState* wa = nullptr;  // launch state of the shared-memory wavefront (RT_PIPELINE_WAVEFRONT_SMEM)
 };
 
 namespace rtb {
+int scene_scratch(RtScene* scene, size_t n_values);  // grow d_accum / d_accum_f / d_rgb to n_values
+// samples [begin, begin + count) of every pixel ADDED into the fixed-point buffer d_accum (memory of scene's device)
+int accumulate_fixed(const RtScene* scene, const RtCamera* cam, const RtParams* params, AccumFx* d_accum, cudaStream_t stream, RtProgressFn cb,
+                     void* user, RtStats* stats, bool sync_for_stats);
 // pipelines: samples [begin, begin+count) of every pixel, ADDED into d_accum; *launches counts kernel launches
-int launch_megakernel(const RtScene* s, const DCamera& cam, const RtParams* p, int begin, int count, float* d_accum, cudaStream_t stream,
+int launch_megakernel(const RtScene* s, const DCamera& cam, const RtParams* p, int begin, int count, AccumFx* d_accum, cudaStream_t stream,
                       RtProgressFn cb, void* user, int* launches);
-int launch_wavefront(RtScene* s, const DCamera& cam, const RtParams* p, int begin, int count, float* d_accum, cudaStream_t stream,
+int launch_wavefront(RtScene* s, const DCamera& cam, const RtParams* p, int begin, int count, AccumFx* d_accum, cudaStream_t stream,
                      RtProgressFn cb, void* user, int* launches);
 void free_wavefront(RtScene* s);
-int launch_warpfront(RtScene* s, const DCamera& cam, const RtParams* p, int begin, int count, float* d_accum, cudaStream_t stream,
-                     RtProgressFn cb, void* user, int* launches);
-bool warpfront_supports(const RtScene* s, const RtParams* p);
-void free_warpfront(RtScene* s);
-int launch_persist(RtScene* s, const DCamera& cam, const RtParams* p, int begin, int count, float* d_accum, cudaStream_t stream,
+int launch_persist(RtScene* s, const DCamera& cam, const RtParams* p, int begin, int count, AccumFx* d_accum, cudaStream_t stream,
                    RtProgressFn cb, void* user, int* launches);
 bool persist_supports(const RtScene* s, const RtParams* p);
 void free_persist(RtScene* s);

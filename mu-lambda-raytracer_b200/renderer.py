@@ -188,12 +188,13 @@ class Renderer:  # raytrace.rs:137-198
 
     def render_arrays(self, logger=None, want_accum=True):
         """One rt_render call with HOST buffers.  Returns (rgb int32 [H,W,3], accum float32 [H,W,3] or None);
-        row 0 is the bottom row.  `logger(done, total)` is called on this thread after each device pass."""
+        row 0 is the bottom row.  `logger(j, H)` is called on this thread once per row index, as Renderer::render does
+        (raytrace.rs:182), paced by the device's progress."""
         p = self._params()
         h, w = p.height, p.width
         rgb = np.empty((h, w, 3), dtype=np.int32)
         accum = np.empty((h, w, 3), dtype=np.float32) if want_accum else None
-        cb = abi.RtProgressFn(lambda done, total, user: logger(done, total)) if logger else abi.RtProgressFn()
+        cb = abi.RtProgressFn(lambda row, total, user: logger(row, total)) if logger else abi.RtProgressFn()
         stats = abi.RtStats()
         abi.check(abi.load().rt_render(self.world.handle, C.byref(self.camera.c), C.byref(p),
                                        accum.ctypes.data_as(C.c_void_p) if want_accum else None,
@@ -204,14 +205,8 @@ class Renderer:  # raytrace.rs:137-198
 
     def render(self, logger=None):
         """Renderer::render: H rows of W (r, g, b) tuples, row j = 0 at the BOTTOM; logger(j, H) called H times."""
-        rgb, _ = self.render_arrays(None, want_accum=False)
-        h = rgb.shape[0]
-        rows = []
-        for j in range(h):
-            rows.append([tuple(int(c) for c in px) for px in rgb[j]])
-            if logger:
-                logger(j, h)
-        return rows
+        rgb, _ = self.render_arrays(logger, want_accum=False)
+        return [[tuple(int(c) for c in px) for px in row] for row in rgb]
 
 
 def to_ppm(rgb):

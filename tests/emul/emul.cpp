@@ -28,7 +28,7 @@ static void make_view(EmulScene& e) {
     for (auto& im : f.images) e.images.push_back(DImage{(unsigned long long)(uintptr_t)im.rgba.data(), im.width, im.height});
     DSceneView& v = e.view;
     v.nodes = f.nodes.data(), v.nodes4 = f.nodes4.empty() ? nullptr : f.nodes4.data(), v.n_nodes4 = (int)f.nodes4.size(), v.prims = f.prims.data(), v.big = f.big.data(), v.inst = f.inst.data();
-    v.mats = f.mats.data(), v.texs = f.texs.data(), v.media = f.media.data();
+    v.mats = f.mats.data(), v.texs = f.texs.data(), v.media = f.media.data(), v.media_prims = f.media_prims.data();
     v.perlin_vec = f.perlin_vec.data(), v.perlin_perm = f.perlin_perm.data(), v.images = e.images.data();
     v.n_nodes = (int)f.nodes.size(), v.n_prims = (int)f.prims.size(), v.n_media = (int)f.media.size();
     v.n_perlin = (int)(f.perlin_vec.size() / (4 * RTB_PERLIN_POINTS));
@@ -109,8 +109,9 @@ void emul_unit_ball(const float* u, int64_t n, float* out) {
     }
 }
 
-// the megakernel's per-thread routine, run row-parallel on host threads; accum = 3*W*H radiance sums
-uint64_t emul_render(void* h, const RtCamera* cam, const RtParams* p, int32_t threads, float* accum) {
+// the megakernel's per-thread routine, run row-parallel on host threads; accum = 3*W*H radiance sums in the library's
+// fixed point (AccumFx: 2^-32 units)
+uint64_t emul_render(void* h, const RtCamera* cam, const RtParams* p, int32_t threads, uint64_t* accum) {
     EmulScene* e = (EmulScene*)h;
     DCamera dc;
     make_camera(*cam, dc);
@@ -125,7 +126,7 @@ uint64_t emul_render(void* h, const RtCamera* cam, const RtParams* p, int32_t th
             int j = next.fetch_add(1);
             if (j >= p->height) break;
             for (int i = 0; i < p->width; ++i) {
-                float sum[3];
+                AccumFx sum[3];
                 uint32_t nr = 0;
                 integrate_item(e->view, dc, P, i, j, p->sample_begin, count, sum, nr);
                 local += nr;

@@ -129,10 +129,48 @@ def case_box_medium(rng, n):  # cornell_smoke's rotated box of smoke
     return b, node, rays
 
 
+def case_unordered_block(rng, n):
+    """Block::new with corners that are not ordered (shapes.rs:173-186 + AARect::new's one-sided normalisation,
+    aarects.rs:31-43): six rects, some of them degenerate — whatever the reference hits, the device must hit"""
+    b = S.DescBuilder()
+    node = b.block((5.0, 3.0, 4.0), (1.0, 6.0, 2.0), _mat(b))
+    rays = S.random_rays(n, rng, [-6, -4, -5], [12, 13, 11], target=[3, 4.5, 3], spread=[2.6, 2.2, 1.6])
+    return b, node, rays
+
+
+def case_two_sphere_medium(rng, n):
+    """ConstantMedium<O: Hittable> (volumes.rs:7-11) with a HittableList of two overlapping spheres as boundary: the
+    medium occupies h1..h2 = the first two crossings of the LIST (volumes.rs:27-34)"""
+    b = S.DescBuilder()
+    m = b.material(abi.RT_MAT_DIELECTRIC, ior=1.5)
+    boundary = b.group(abi.RT_NODE_LIST, [b.sphere((0.0, 0.0, 0.0), 30.0, m), b.sphere((35.0, 5.0, 0.0), 25.0, m)])
+    node = b.medium(boundary, 0.05, (0.8, 0.8, 0.8))
+    rays = S.random_rays(n, rng, [-90, -70, -70], [110, 70, 70], target=[15, 2, 0], spread=[45, 30, 30])
+    return b, node, rays
+
+
+def case_sphere_and_box_medium(rng, n):  # a BVH of a sphere and a rotated, translated block as boundary
+    b = S.DescBuilder()
+    m = b.material(abi.RT_MAT_DIELECTRIC, ior=1.5)
+    blk = b.translate((20.0, -10.0, 5.0), b.rotate(1, 25.0, b.block((0.0, 0.0, 0.0), (40.0, 30.0, 20.0), m)))
+    boundary = b.group(abi.RT_NODE_BVH, [b.sphere((0.0, 0.0, 0.0), 22.0, m), blk])
+    node = b.medium(boundary, 0.02, (1, 1, 1))
+    rays = S.random_rays(n, rng, [-80, -60, -60], [110, 70, 80], target=[20, 5, 10], spread=[40, 25, 25])
+    return b, node, rays
+
+
+def case_unordered_block_medium(rng, n):  # the six-rect form of a block as a medium boundary
+    b = S.DescBuilder()
+    node = b.medium(b.block((50.0, 0.0, 40.0), (10.0, 60.0, 5.0), _mat(b)), 0.03, (1, 1, 1))
+    rays = S.random_rays(n, rng, [-60, -50, -60], [120, 110, 100], target=[30, 30, 22], spread=[26, 35, 22])
+    return b, node, rays
+
+
 SURFACE_CASES = [case_small_sphere, case_sphere_from_inside, case_negative_radius_sphere, case_ground_sphere,
                  case_fog_sphere_from_inside, case_xy_rect, case_xz_rect, case_yz_rect, case_block, case_block_from_inside,
-                 case_rotated_translated_block, case_rotated_only_block, case_rotate_x_translate_sphere]
-MEDIUM_CASES = [case_sphere_medium, case_fog_medium, case_box_medium]
+                 case_rotated_translated_block, case_rotated_only_block, case_rotate_x_translate_sphere, case_unordered_block]
+MEDIUM_CASES = [case_sphere_medium, case_fog_medium, case_box_medium, case_two_sphere_medium, case_sphere_and_box_medium,
+                case_unordered_block_medium]
 
 
 def compare_surface(g, o, rays, grazing=0.02, tol=1e-5):

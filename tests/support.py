@@ -201,13 +201,17 @@ class EmulScene:
         a["prim"][ok] = self.prim_nodes[a["prim"][ok]]
         return a
 
-    def render(self, cam, width, height, spp, max_depth=50, seed=42, threads=0, sample_begin=0):
+    def render(self, cam, width, height, spp, max_depth=50, seed=42, threads=0, sample_begin=0, fixed=False):
+        """radiance sums per pixel: float32 (as rt_render's accum_rgb), or with fixed=True the library's native 64-bit
+        fixed-point sums (2^-32 units) as uint64"""
         p = abi.RtParams()
         p.width, p.height, p.samples_per_pixel, p.max_depth = width, height, spp, max_depth
         p.seed, p.sample_begin, p.sample_count = seed, sample_begin, spp
-        accum = np.zeros((height, width, 3), dtype=np.float32)
+        accum = np.zeros((height, width, 3), dtype=np.uint64)
         rays = emul().emul_render(self.h, C.byref(cam.c), C.byref(p), threads, accum.ctypes.data)
-        return accum, rays
+        if fixed:
+            return accum, rays
+        return (accum.astype(np.float64) / abi.RT_ACCUM_FIXED_ONE).astype(np.float32), rays
 
     def close(self):
         if self.h:

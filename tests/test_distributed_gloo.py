@@ -1,6 +1,7 @@
 """The N > 1 host logic on CPU: world_size-2 gloo process group, sample-slice sharding and the single reduce.
-Each rank integrates its slice with the host build of the device code (tests/emul); the reduced buffer must equal
-the single-process sum of the two slices, and the slices must tile the sample range exactly."""
+Each rank integrates its slice with the host build of the device code (tests/emul) into the library's fixed-point sums;
+the reduced buffer must equal — exactly — what one process renders for the whole sample range, and the slices must
+tile the range."""
 import os
 import socket
 import sys
@@ -44,12 +45,12 @@ def _worker(rank, world, port, out_dir):
         W = H = 24
         spp = 9
         begin, count = sample_slice(spp, world, rank)
-        part, _ = es.render(cam, W, H, count, seed=11, threads=1, sample_begin=begin)
+        part, _ = es.render(cam, W, H, count, seed=11, threads=1, sample_begin=begin, fixed=True)
         np.save(os.path.join(out_dir, f"part{rank}.npy"), part)
-        t = torch.from_numpy(part.copy())
+        t = torch.from_numpy(part.view(np.int64).copy())  # what distributed.render_sharded reduces: int64 sums
         reduce_accumulation(t, dst=0)
         if rank == 0:
-            np.save(os.path.join(out_dir, "reduced.npy"), t.numpy())
+            np.save(os.path.join(out_dir, "reduced.npy"), t.numpy().view(np.uint64))
     finally:
         dist.destroy_process_group()
 
@@ -62,7 +63,7 @@ def test_two_rank_reduce_matches_single_process(tmp_path):
     mp.spawn(_worker, args=(2, port, str(tmp_path)), nprocs=2, join=True)
     p0, p1 = np.load(tmp_path / "part0.npy"), np.load(tmp_path / "part1.npy")
     red = np.load(tmp_path / "reduced.npy")
-    assert np.array_equal(red, p0 + p1)  # one float add per value: deterministic
+    assert np.array_equal(red, p0 + p1)  # integer sums: exact
     # and the two slices together are the same paths a single process would have traced
     sys.path.insert(0, os.path.join(ROOT, "tests"))
     import mu_lambda_raytracer_b200 as rt
@@ -72,5 +73,5 @@ def test_two_rank_reduce_matches_single_process(tmp_path):
     es = S.EmulScene(desc.ptr)
     info = world_obj.camera()
     cam = S.make_camera(info["lookfrom"], info["lookat"], info["field_of_view"], 1.0)
-    full, _ = es.render(cam, 24, 24, 9, seed=11, threads=1)
-    assert np.allclose(full, red, rtol=1e-5, atol=1e-5)
+    full, _ = es.render(cam, 24, 24, 9, seed=11, threads=1, fixed=True)
+    assert np.array_equal(full, red)  # fixed-point accumulation: the split over ranks does not change a single bit

@@ -77,8 +77,7 @@ def test_closest_hit_matches_oracle(name, layout):
     scene.close()
 
 
-PIPELINES = {"megakernel": abi.RT_PIPELINE_MEGAKERNEL, "wavefront": abi.RT_PIPELINE_WAVEFRONT,
-             "wavefront_smem": abi.RT_PIPELINE_WAVEFRONT_SMEM, "persistent": abi.RT_PIPELINE_PERSISTENT}
+PIPELINES = {"megakernel": abi.RT_PIPELINE_MEGAKERNEL, "wavefront": abi.RT_PIPELINE_WAVEFRONT, "persistent": abi.RT_PIPELINE_PERSISTENT}
 
 
 @pytest.mark.parametrize("pipeline", list(PIPELINES))
@@ -132,7 +131,7 @@ def test_wavefront_and_megakernel_agree(name, aspect):
         rgb, accum = r.render_arrays()
         out[pname] = (rgb, accum.astype(np.float64), r.stats)
     a = out["megakernel"]
-    for other in ("wavefront", "wavefront_smem", "persistent"):
+    for other in ("wavefront", "persistent"):
         b = out[other]
         assert a[2]["paths"] == b[2]["paths"] == W * H * spp
         assert abs(a[2]["rays"] - b[2]["rays"]) <= 1e-3 * a[2]["rays"], other
@@ -156,7 +155,7 @@ def test_wavefront_many_rounds_small_pool(monkeypatch):
         r.pipeline = pid
         _, accum = r.render_arrays()
         res[pname] = (accum.astype(np.float64), r.stats)
-    for other in ("wavefront", "wavefront_smem", "persistent"):
+    for other in ("wavefront", "persistent"):
         assert abs(res["megakernel"][1]["rays"] - res[other][1]["rays"]) <= 2e-3 * res["megakernel"][1]["rays"]
         close = np.isclose(res["megakernel"][0], res[other][0], rtol=1e-4, atol=1e-3).all(axis=2)
         assert close.mean() > 0.97, (other, close.mean())

@@ -61,7 +61,7 @@ def test_medium_interval_matches_oracle_1m_rays(case):
     dlen = np.linalg.norm(rays[:, 3:6], axis=1)
     scale = np.abs(rays[:, :3]).max(axis=1) + 1000.0
     both = (ohit == 1) & ghit
-    assert both.sum() > 0.2 * len(rays)
+    assert both.sum() > (0.05 if "unordered" in case.__name__ else 0.2) * len(rays)  # degenerate sides: few two-crossing rays
     assert ((ohit == 1) != ghit).sum() <= 100  # only chords within rounding of the 0.001 re-entry epsilon
     assert np.all(np.abs(g["t"][both] - ot[both, 0]) * dlen[both] <= 2e-5 * scale[both])
     assert np.all(np.abs(g["u"][both] - ot[both, 1]) * dlen[both] <= 2e-5 * scale[both])

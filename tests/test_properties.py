@@ -64,7 +64,7 @@ def test_white_furnace_oracle_and_emulated_device_math():
 
 
 @pytest.mark.gpu
-@pytest.mark.parametrize("pipeline", [abi.RT_PIPELINE_PERSISTENT, abi.RT_PIPELINE_WAVEFRONT, abi.RT_PIPELINE_MEGAKERNEL, abi.RT_PIPELINE_WAVEFRONT_SMEM])
+@pytest.mark.parametrize("pipeline", [abi.RT_PIPELINE_PERSISTENT, abi.RT_PIPELINE_WAVEFRONT, abi.RT_PIPELINE_MEGAKERNEL])
 def test_white_furnace_on_device(pipeline):
     b, desc = furnace_desc()
     scene = rt.Scene(rt.SceneDescription(desc, owned=False))
