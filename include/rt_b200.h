@@ -279,6 +279,32 @@ void rt_sample_slice(int32_t sample_begin, int32_t sample_count, int32_t n_parts
 int rt_intersect_batch(const RtScene* scene, int32_t node, const float* rays, int64_t n, RtHit* out);
 
 /*
+ * Material::scatter / Material::emit (materials.rs:7-11; impls :25-127, volumes.rs:77-83) for a batch of fixed hits
+ * (test entry point, SURVEY §8c level 2 for the shade stage).  The caller supplies the hit record (p, the face-forwarded
+ * normal, u, v, front_face as hittable.rs:7-15 holds them), the incoming ray and the four uniforms the device would draw
+ * for this event: uniform[0..2] -> the in-ball sample of Lambertian / fuzzy Metal / Isotropic (z = 1 - 2 u0,
+ * azimuth 2 pi u1, radius cbrt(u2): the direct sampler that replaces vec.rs:23-30's rejection loop), uniform[3] -> the
+ * Dielectric's reflect-or-refract draw (materials.rs:98).
+ *   scattered = 1: attenuation and the scattered ray's direction (its origin is p); emitted = 0
+ *   scattered = 0: emitted = Material::emit (DiffuseLight: its texture, both faces; everything else 0)
+ */
+typedef struct RtScatterIn {
+    float ray_origin[3], ray_dir[3];
+    float p[3], normal[3];
+    float u, v;
+    int32_t front_face;
+    int32_t material; /* index into desc.materials */
+    float uniform[4];
+} RtScatterIn;
+typedef struct RtScatterOut {
+    int32_t scattered;
+    float attenuation[3];
+    float dir[3];
+    float emitted[3];
+} RtScatterOut;
+int rt_scatter_batch(const RtScene* scene, const RtScatterIn* in, int64_t n, RtScatterOut* out);
+
+/*
  * Texture::value (textures.rs:4-6) for a batch (test entry point).
  *   texture: index into desc.textures; uvp: N x 5 floats (u, v, p.x, p.y, p.z); out: N x 3 floats.
  */
@@ -292,6 +318,22 @@ int rt_texture_value_batch(const RtScene* scene, int32_t texture, const float* u
  */
 int rt_generate_rays(const RtCamera* cam, const RtParams* params, const int32_t* pixel, const int32_t* sample,
                      int64_t n, float* out_rays, float* out_sample);
+
+/*
+ * Measured ceilings of a device for the roofline the render kernels are quoted against (bench.py): dependent-FFMA
+ * chains on every SM (scalar FFMA and packed FFMA2, 2 flops per multiply-add) and repeated reads of an L2-resident
+ * 32 MB buffer; best of several CUDA-event-timed launches each.  Measurement aid; not on the render path.
+ */
+typedef struct RtPeaks {
+    double fp32_ffma_tflops;        /* scalar FFMA chains */
+    double fp32_ffma2_tflops;       /* packed FFMA2 chains (sm_100) */
+    double fp32_theoretical_tflops; /* SMs x 128 lanes x 2 x the device's maximum SM clock */
+    double l2_read_gbs;
+    double sm_clock_mhz;            /* cudaDevAttrClockRate */
+    int32_t sm_count;
+    int32_t reserved;
+} RtPeaks;
+int rt_measure_peaks(int device, RtPeaks* out);
 
 /* ---- host side above the ABI: worlds.rs restated against the description ---- */
 

@@ -71,10 +71,24 @@ class RtHit(C.Structure):
                 ("front_face", C.c_int32), ("material", C.c_int32), ("prim", C.c_int32)]
 
 
+class RtScatterIn(C.Structure):
+    _fields_ = [("ray_origin", C.c_float * 3), ("ray_dir", C.c_float * 3), ("p", C.c_float * 3), ("normal", C.c_float * 3),
+                ("u", C.c_float), ("v", C.c_float), ("front_face", C.c_int32), ("material", C.c_int32), ("uniform", C.c_float * 4)]
+
+
+class RtScatterOut(C.Structure):
+    _fields_ = [("scattered", C.c_int32), ("attenuation", C.c_float * 3), ("dir", C.c_float * 3), ("emitted", C.c_float * 3)]
+
+
 class RtStats(C.Structure):
     _fields_ = [("paths", C.c_uint64), ("rays", C.c_uint64), ("device_ms", C.c_double),
                 ("kernel_launches", C.c_int32), ("pipeline_used", C.c_int32), ("bvh_layout_used", C.c_int32),
                 ("reserved", C.c_int32)]
+
+
+class RtPeaks(C.Structure):
+    _fields_ = [("fp32_ffma_tflops", C.c_double), ("fp32_ffma2_tflops", C.c_double), ("fp32_theoretical_tflops", C.c_double),
+                ("l2_read_gbs", C.c_double), ("sm_clock_mhz", C.c_double), ("sm_count", C.c_int32), ("reserved", C.c_int32)]
 
 
 class RtWorldInfo(C.Structure):
@@ -108,9 +122,11 @@ PROTOTYPES = {
     "rt_accum_fixed_to_float_device": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int64, C.c_int, C.c_void_p]),
     "rt_release_cached_memory": (None, []),
     "rt_intersect_batch": (C.c_int, [C.c_void_p, C.c_int32, C.c_void_p, C.c_int64, C.POINTER(RtHit)]),
+    "rt_scatter_batch": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p]),
     "rt_texture_value_batch": (C.c_int, [C.c_void_p, C.c_int32, C.c_void_p, C.c_int64, C.c_void_p]),
     "rt_generate_rays": (C.c_int, [C.POINTER(RtCamera), C.POINTER(RtParams), C.c_void_p, C.c_void_p, C.c_int64,
                                    C.c_void_p, C.c_void_p]),
+    "rt_measure_peaks": (C.c_int, [C.c_int, C.POINTER(RtPeaks)]),
     "rt_world_count": (C.c_int, []),
     "rt_world_name": (C.c_char_p, [C.c_int]),
     "rt_world_info": (C.c_int, [C.c_char_p, C.POINTER(RtWorldInfo)]),

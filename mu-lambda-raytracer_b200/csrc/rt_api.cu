@@ -86,6 +86,15 @@ __global__ void texture_kernel(DSceneView S, int tex, const float* __restrict__ 
     rgb[3 * i] = c.x, rgb[3 * i + 1] = c.y, rgb[3 * i + 2] = c.z;
 }
 
+__global__ void scatter_kernel(DSceneView S, const RtScatterIn* __restrict__ in, long long n, RtScatterOut* __restrict__ out) {
+    long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    RtScatterIn q = in[i];
+    RtScatterOut o;
+    scatter_query(S, q, o);
+    out[i] = o;
+}
+
 __global__ void camera_kernel(DCamera cam, DRenderParams P, const int32_t* __restrict__ pixel, const int32_t* __restrict__ sample, long long n,
                               float* __restrict__ rays, float* __restrict__ us) {
     long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
@@ -183,6 +192,8 @@ int upload_scene(RtScene* s) {
     v.perlin_vec = pvec, v.perlin_perm = pperm, v.images = dimages;
     v.n_nodes = (int)f.nodes.size(), v.n_prims = (int)f.prims.size(), v.n_media = (int)f.media.size();
     v.n_perlin = (int)(f.perlin_vec.size() / (4 * RTB_PERLIN_POINTS));
+    v.media_general = f.media.size() > 4 ? 1 : 0;
+    for (const auto& m : f.media) v.media_general |= m.count > 1 ? 1 : 0;
     v.bg_kind = f.bg_kind;
     for (int k = 0; k < 3; ++k) v.bg_top[k] = f.bg_top[k], v.bg_bottom[k] = f.bg_bottom[k];
     return RT_OK;
@@ -597,6 +608,35 @@ int rt_texture_value_batch(const RtScene* scene, int32_t texture, const float* u
             break;
         }
         cudaMemcpy(out_rgb, d_out, (size_t)n * 3 * sizeof(float), cudaMemcpyDeviceToHost);
+    } while (0);
+    cudaFree(d_in);
+    cudaFree(d_out);
+    return rc;
+}
+
+int rt_scatter_batch(const RtScene* scene, const RtScatterIn* in, int64_t n, RtScatterOut* out) {
+    if (!scene || !in || !out || n < 0) return set_error(RT_ERR_INVALID, "rt_scatter_batch: bad argument");
+    if (n == 0) return RT_OK;
+    const int n_mats = (int)scene->flat.mats.size();
+    for (int64_t i = 0; i < n; ++i)
+        if (in[i].material < 0 || in[i].material >= n_mats) return set_error(RT_ERR_INVALID, "rt_scatter_batch: material %d out of range", in[i].material);
+    DeviceGuard g(scene->device);
+    RtScatterIn* d_in = nullptr;
+    RtScatterOut* d_out = nullptr;
+    int rc = RT_OK;
+    do {
+        if (cudaMalloc(&d_in, (size_t)n * sizeof(RtScatterIn)) != cudaSuccess || cudaMalloc(&d_out, (size_t)n * sizeof(RtScatterOut)) != cudaSuccess) {
+            rc = set_error(RT_ERR_CUDA, "rt_scatter_batch: cudaMalloc failed");
+            break;
+        }
+        cudaMemcpy(d_in, in, (size_t)n * sizeof(RtScatterIn), cudaMemcpyHostToDevice);
+        scatter_kernel<<<(unsigned)((n + 127) / 128), 128>>>(scene->view, d_in, n, d_out);
+        cudaError_t e = cudaDeviceSynchronize();
+        if (e != cudaSuccess) {
+            rc = set_error(RT_ERR_CUDA, "rt_scatter_batch: kernel failed: %s", cudaGetErrorString(e));
+            break;
+        }
+        cudaMemcpy(out, d_out, (size_t)n * sizeof(RtScatterOut), cudaMemcpyDeviceToHost);
     } while (0);
     cudaFree(d_in);
     cudaFree(d_out);

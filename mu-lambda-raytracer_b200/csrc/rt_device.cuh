@@ -44,8 +44,16 @@ RTB_DEV F8 ld8(const void* p) {
 }
 RTB_DEV uint32_t mulhi32(uint32_t a, uint32_t b) { return __umulhi(a, b); }
 RTB_DEV float u32_to_unit(uint32_t x) { return __uint2float_rz(x) * 2.3283064365386963e-10f; }
-RTB_DEV void sincos_2pi(float x, float* s, float* c) { sincospif(2.0f * x, s, c); }
+// sin / cos of 2 pi x for x in [0, 1): the hardware approximations (MUFU.SIN / MUFU.COS, abs. error 2^-21.4 on [-pi, pi])
+// of the angle shifted into [-pi, pi), negated back.  Explicit intrinsics: the library is built WITHOUT --use_fast_math
+// (build.py), so that the libm names elsewhere (the checker's and the marble's sinf, acosf, atan2f) stay accurate.
+RTB_DEV void sincos_2pi(float x, float* s, float* c) {
+    float sn, cs;
+    __sincosf(fmaf(x, 6.2831853071795865f, -3.1415926535897932f), &sn, &cs);
+    *s = -sn, *c = -cs;
+}
 RTB_DEV float fast_cbrt(float x) { return __powf(x, 0.33333334f); }
+RTB_DEV float sin_small(float x) { return __sinf(x); }  // |x| <= pi: MUFU.SIN, abs. error 2^-21.4
 RTB_DEV float fast_log(float x) { return __logf(x); }
 RTB_DEV float as_float(uint32_t u) { return __uint_as_float(u); }
 RTB_DEV uint32_t as_uint(float f) { return __float_as_uint(f); }
@@ -85,6 +93,7 @@ inline void sincos_2pi(float x, float* s, float* c) {
     *s = sinf(6.283185307179586f * x), *c = cosf(6.283185307179586f * x);
 }
 inline float fast_cbrt(float x) { return cbrtf(x); }
+inline float sin_small(float x) { return sinf(x); }
 inline float fast_log(float x) { return logf(x); }
 inline float as_float(uint32_t u) {
     float f;
@@ -599,38 +608,79 @@ RTB_DEV_NOINLINE V3 compound_boundary(const DSceneView& S, int first, int count,
 }
 
 // deterministic part: the boundary interval clipped to [tmin, tmax]
-RTB_DEV bool medium_interval(const DSceneView& S, const PrimRec& b, int first, int count, const Ray& r, float tmin, float tmax, float& t1, float& t2) {
-    float te, tx;
-    if (count > 1) {
-        const V3 h = compound_boundary(S, first, count, r.o.x, r.o.y, r.o.z, r.d.x, r.d.y, r.d.z);
-        te = h.x, tx = h.y;
-        if (!(tx < RTB_INF)) return false;
-    } else {
-        if (!boundary_crossings(S, b, r, te, tx)) return false;
-        if (!(tx >= te + 0.001f)) return false;  // second boundary.hit(h1.t + 0.001, inf) finds nothing
-    }
+RTB_DEV bool clip_interval(float te, float tx, float tmin, float tmax, float& t1, float& t2) {
     t1 = fmaxf(te, tmin), t2 = fminf(tx, tmax);
     if (t1 >= t2) return false;
     t1 = fmaxf(t1, 0.0f);
     return true;
 }
+// single-primitive boundary (every shipped world): entry and exit of that primitive
+RTB_DEV bool medium_interval(const DSceneView& S, const PrimRec& b, const Ray& r, float tmin, float tmax, float& t1, float& t2) {
+    float te, tx;
+    if (!boundary_crossings(S, b, r, te, tx)) return false;
+    if (!(tx >= te + 0.001f)) return false;  // second boundary.hit(h1.t + 0.001, inf) finds nothing
+    return clip_interval(te, tx, tmin, tmax, t1, t2);
+}
+RTB_DEV bool medium_interval_any(const DSceneView& S, const DMedium* M, const Ray& r, float tmin, float tmax, float& t1, float& t2) {
+    if (M->count <= 1) return medium_interval(S, load_prim16(&M->boundary), r, tmin, tmax, t1, t2);
+    const V3 h = compound_boundary(S, M->first, M->count, r.o.x, r.o.y, r.o.z, r.d.x, r.d.y, r.d.z);
+    if (!(h.y < RTB_INF)) return false;
+    return clip_interval(h.x, h.y, tmin, tmax, t1, t2);
+}
 
 // free-flight sampling in every medium; keeps the closest event.  Medium m uses uniform m & 3 of Philox block
 // (pixel, sample, draw, tag + (m >> 2)): scenes with up to four media draw exactly one block per segment.
-RTB_DEV void sample_media(const DSceneView& S, const Ray& r, float tmin, const PathRng& rng, float& t_best, int& medium_best) {
-    medium_best = -1;
-    float len = sqrtf(dot(r.d, r.d));
-    float u[4];
+// The general form — any number of media, boundaries of several primitives — is out of line: the kernels take it only
+// for scenes that need it (DSceneView.media_general), so that the common case keeps its registers.
+struct MediaEvent {
+    float t;
+    int medium;
+};
+RTB_DEV_NOINLINE MediaEvent sample_media_general(const DSceneView& S, float ox, float oy, float oz, float dx, float dy, float dz, float tmin, uint32_t pixel,
+                                                 uint32_t sample, uint32_t draw, uint32_t k0, uint32_t k1, float t_best) {
+    Ray r;
+    r.o = v3(ox, oy, oz), r.d = v3(dx, dy, dz);
+    PathRng rng;
+    rng.pixel = pixel, rng.sample = sample, rng.draw = draw, rng.k0 = k0, rng.k1 = k1;
+    MediaEvent ev;
+    ev.t = t_best, ev.medium = -1;
+    const float len = sqrtf(dot(r.d, r.d));
+    float u[4] = {0.f, 0.f, 0.f, 0.f};
     for (int m = 0; m < S.n_media; ++m) {
         if ((m & 3) == 0) rng_block(rng, (uint32_t)(m >> 2), u);
         const DMedium* M = S.media + m;
-        PrimRec b = load_prim16(&M->boundary);
-        float4 tail = ld4(reinterpret_cast<const char*>(M) + 32);  // neg_inv_density, mat, first, count
         float t1, t2;
-        if (!medium_interval(S, b, (int)as_uint(tail.z), (int)as_uint(tail.w), r, tmin, t_best, t1, t2)) continue;
+        if (!medium_interval_any(S, M, r, tmin, ev.t, t1, t2)) continue;
+        const float um = (m & 3) == 0 ? u[0] : ((m & 3) == 1 ? u[1] : ((m & 3) == 2 ? u[2] : u[3]));
+        const float dist = M->neg_inv_density * fast_log(um);
+        if (dist > (t2 - t1) * len) continue;
+        ev.t = t1 + dist / len, ev.medium = m;
+    }
+    return ev;
+}
+// MODE: MEDIA_FAST = the caller knows the scene is not "general" (no call site for the out-of-line form: a call in the
+// persistent kernel's shade phase costs it 240 B of stack frame and 150 B of spills), MEDIA_GENERAL = it knows it is,
+// MEDIA_ANY = decide here from the scene's flag.
+enum { MEDIA_FAST = 0, MEDIA_GENERAL = 1, MEDIA_ANY = 2 };
+template <int MODE = MEDIA_ANY>
+RTB_DEV void sample_media(const DSceneView& S, const Ray& r, float tmin, const PathRng& rng, float& t_best, int& medium_best) {
+    if (MODE == MEDIA_GENERAL || (MODE == MEDIA_ANY && S.media_general)) {
+        const MediaEvent ev = sample_media_general(S, r.o.x, r.o.y, r.o.z, r.d.x, r.d.y, r.d.z, tmin, rng.pixel, rng.sample, rng.draw, rng.k0, rng.k1, t_best);
+        t_best = ev.t, medium_best = ev.medium;
+        return;
+    }
+    medium_best = -1;
+    float len = sqrtf(dot(r.d, r.d));
+    float u[4];
+    rng_block(rng, 0u, u);
+    for (int m = 0; m < S.n_media; ++m) {  // <= 4 media, one primitive per boundary
+        const DMedium* M = S.media + m;
+        PrimRec b = load_prim16(&M->boundary);
+        float4 tail = ld4(reinterpret_cast<const char*>(M) + 32);
+        float t1, t2;
+        if (!medium_interval(S, b, r, tmin, t_best, t1, t2)) continue;
         float inside = (t2 - t1) * len;
-        float um = (m & 3) == 0 ? u[0] : ((m & 3) == 1 ? u[1] : ((m & 3) == 2 ? u[2] : u[3]));
-        float dist = tail.x * fast_log(um);  // neg_inv_density * ln(U)
+        float dist = tail.x * fast_log(u[m]);  // neg_inv_density * ln(U)
         if (dist > inside) continue;
         t_best = t1 + dist / len;
         medium_best = m;
@@ -691,8 +741,21 @@ struct NoiseReq {
     V3 p;     // the hit point (unscaled)
 };
 
+// Accurate sine for the two textures whose LOOK depends on it: the checker's sin(5x) at |5x| up to thousands of radians
+// (the hardware sine alone loses the phase out there: its error grows with |x|) and the marble's phase.  Two-term
+// Cody-Waite reduction to [-pi/2, pi/2] with FMAs (exact to the input's own rounding for |x| < 2^23), then the hardware
+// sine where it is good to 2^-21.4 absolute: ~8 instructions instead of libm's ~100 (four inlined copies of which cost
+// the persistent kernel 8 % through its instruction footprint; profiles/r2_fastmath_ab.txt).
+RTB_DEV float sin_accurate(float x) {
+    const float k = rintf(x * 0.318309886183790672f);
+    float r = fmaf(k, -3.14159274101257324f, x);  // pi = 3.14159274101257324 - 8.74227765734758577e-8 - ...
+    r = fmaf(k, 8.74227765734758577e-8f, r);
+    const float s = sin_small(r);
+    return ((int)k & 1) ? -s : s;
+}
+
 RTB_DEV float noise_value(const DTexture& T, V3 p, float turbulence) {  // NoiseTexture::value, textures.rs:163-166 — marble phase on z
-    return 0.5f * (1.0f + sinf(T.scale * p.z + 10.0f * turbulence));
+    return 0.5f * (1.0f + sin_accurate(T.scale * p.z + 10.0f * turbulence));
 }
 
 // req == nullptr: evaluate everything here.  Otherwise a NOISE leaf is left pending in *req and white is returned.
@@ -724,7 +787,7 @@ RTB_DEV V3 texture_leaf(const DSceneView& S, int tex, float u, float v, V3 p, No
 
 RTB_DEV V3 texture_value(const DSceneView& S, int tex, float u, float v, V3 p, NoiseReq* req = nullptr) {
     if (S.texs[tex].kind == TEX_CHECKER) {  // textures.rs:40-49; nested checkers see the same p, hence the same side
-        const float sines = sinf(5.0f * p.x) * sinf(5.0f * p.y) * sinf(5.0f * p.z);
+        const float sines = sin_accurate(5.0f * p.x) * sin_accurate(5.0f * p.y) * sin_accurate(5.0f * p.z);
         for (int level = 0; level < RTB_CHECKER_DEPTH && S.texs[tex].kind == TEX_CHECKER; ++level) tex = sines < 0.0f ? S.texs[tex].a : S.texs[tex].b;
     }
     return texture_leaf(S, tex, u, v, p, req);
@@ -996,6 +1059,7 @@ RTB_DEV float4 f4(float x, float y, float z, float w) {
 
 // the closest medium event along the slot's (new) ray, drawn with the media uniforms of segment `segment`; it
 // becomes the t_max (and fallback hit code) of the surface search in the extend stage
+template <int MODE = MEDIA_ANY>
 RTB_DEV void wf_presample_media(const DSceneView& S, const DRenderParams& P, WfSlot& s, int segment) {
     float t = RTB_INF;
     int medium = -1;
@@ -1004,7 +1068,7 @@ RTB_DEV void wf_presample_media(const DSceneView& S, const DRenderParams& P, WfS
         r.o = v3(s.A.x, s.A.y, s.A.z), r.d = v3(s.B.x, s.B.y, s.B.z);
         PathRng rng;
         rng.pixel = as_uint(s.A.w), rng.sample = as_uint(s.C.w), rng.draw = 1u + 2u * (uint32_t)segment, rng.k0 = P.seed_lo, rng.k1 = P.seed_hi;
-        sample_media(S, r, RTB_T_MIN, rng, t, medium);
+        sample_media<MODE>(S, r, RTB_T_MIN, rng, t, medium);
     }
     s.D.x = t;
     s.D.y = as_float(medium >= 0 ? (uint32_t)(WF_MEDIUM | medium) : 0xFFFFFFFFu);
@@ -1115,9 +1179,8 @@ RTB_DEV void intersect_query(const DSceneView& S, int mode, const float* q, RtHi
     out.p[0] = out.p[1] = out.p[2] = 0.f;
     out.normal[0] = out.normal[1] = out.normal[2] = 0.f;
     if (mode == QUERY_MEDIUM) {
-        PrimRec b = load_prim16(&S.media[0].boundary);
         float t1, t2;
-        if (medium_interval(S, b, S.media[0].first, S.media[0].count, r, tmin, tmax, t1, t2)) out.t = t1, out.u = t2, out.material = S.media[0].mat;
+        if (medium_interval_any(S, S.media, r, tmin, tmax, t1, t2)) out.t = t1, out.u = t2, out.material = S.media[0].mat;
         return;
     }
     float t;
@@ -1132,6 +1195,22 @@ RTB_DEV void intersect_query(const DSceneView& S, int mode, const float* q, RtHi
     out.t = t, out.u = s.u, out.v = s.v, out.front_face = s.front ? 1 : 0, out.material = P.mat, out.prim = prim;
     out.p[0] = s.p.x, out.p[1] = s.p.y, out.p[2] = s.p.z;
     out.normal[0] = s.n.x, out.normal[1] = s.n.y, out.normal[2] = s.n.z;
+}
+
+// Material::scatter / emit for one caller-supplied hit (rt_scatter_batch): the very `scatter` the pipelines call
+RTB_DEV void scatter_query(const DSceneView& S, const RtScatterIn& in, RtScatterOut& out) {
+    Surface sf;
+    sf.p = v3(in.p[0], in.p[1], in.p[2]), sf.n = v3(in.normal[0], in.normal[1], in.normal[2]);
+    sf.u = in.u, sf.v = in.v, sf.front = in.front_face != 0;
+    PathState ps;
+    ps.ray.o = v3(in.ray_origin[0], in.ray_origin[1], in.ray_origin[2]), ps.ray.d = v3(in.ray_dir[0], in.ray_dir[1], in.ray_dir[2]);
+    ps.beta = v3(1.f, 1.f, 1.f), ps.origin_prim = -1, ps.origin_face = 0, ps.depth = 1;
+    V3 radiance = v3(0.f, 0.f, 0.f);
+    const bool alive = scatter(S, S.mats[in.material], sf, in.uniform, ps, -1, 0, radiance, nullptr);
+    out.scattered = alive ? 1 : 0;
+    out.attenuation[0] = alive ? ps.beta.x : 0.f, out.attenuation[1] = alive ? ps.beta.y : 0.f, out.attenuation[2] = alive ? ps.beta.z : 0.f;
+    out.dir[0] = alive ? ps.ray.d.x : 0.f, out.dir[1] = alive ? ps.ray.d.y : 0.f, out.dir[2] = alive ? ps.ray.d.z : 0.f;
+    out.emitted[0] = alive ? 0.f : radiance.x, out.emitted[1] = alive ? 0.f : radiance.y, out.emitted[2] = alive ? 0.f : radiance.z;
 }
 
 // the camera ray of (pixel, sample) exactly as integrate_item generates it

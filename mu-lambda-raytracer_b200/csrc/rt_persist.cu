@@ -138,7 +138,7 @@ enum { PSS_SHADE_PHASES, PSS_SHADE_ACT, PSS_SHADE_DONE, PSS_SHADE_ONPARK, PSS_EX
 // Dynamic shared memory: [pool PS_SLOTS x PS_REC x NT floats][stack SD x NT keys][nodes4][prims].
 #define PS_SCENE_NODES 1
 #define PS_SCENE_PRIMS 2
-template <bool STATS, bool WIDE, int SD, int NT, int SCENE>
+template <bool STATS, bool WIDE, int SD, int NT, int SCENE, int MEDIA>
 __global__ void __launch_bounds__(NT, (STATS || NT > 128) ? 1 : PS_MIN_BLOCKS) persist_kernel(DSceneView S, DCamera cam, DRenderParams P, PsCounters* __restrict__ ctr,
                                                              AccumFx* __restrict__ accum, unsigned long long* __restrict__ rays_out,
                                                              unsigned int chunk_size, unsigned long long* __restrict__ stats, PsTune tune) {
@@ -274,9 +274,15 @@ __global__ void __launch_bounds__(NT, (STATS || NT > 128) ? 1 : PS_MIN_BLOCKS) p
             }
             if (shade && !alive) {  // the path ended: beta * (emission | background | 0) -> its pixel
                 AccumFx* dst = accum + 3 * (size_t)pixel_out;  // 64-bit integer REDs: order-independent sums
+#ifdef RTB_AB_FLOAT_RED  // timing A/B only (build flavor "floatred"): round 1's 32-bit float REDs into the same slots; the image is garbage
+                if (radiance.x != 0.f) atomicAdd(reinterpret_cast<float*>(dst + 0), radiance.x);
+                if (radiance.y != 0.f) atomicAdd(reinterpret_cast<float*>(dst + 1), radiance.y);
+                if (radiance.z != 0.f) atomicAdd(reinterpret_cast<float*>(dst + 2), radiance.z);
+#else
                 if (radiance.x != 0.f) atomicAdd(dst + 0, radiance_fixed(radiance.x));
                 if (radiance.y != 0.f) atomicAdd(dst + 1, radiance_fixed(radiance.y));
                 if (radiance.z != 0.f) atomicAdd(dst + 2, radiance_fixed(radiance.z));
+#endif
             }
             // regenerate: the next camera paths of the job, handed out in reservation order
             bool need = act && !alive;
@@ -315,7 +321,7 @@ __global__ void __launch_bounds__(NT, (STATS || NT > 128) ? 1 : PS_MIN_BLOCKS) p
             // survivors and fresh camera paths alike: media event of the new ray, then "ready"
             if (act) {
                 if (alive) {
-                    wf_presample_media(S, P, s, segment_next);
+                    wf_presample_media<MEDIA>(S, P, s, segment_next);
                     rec_store<NT>(pool, s_work, s);
                     stat = slot_set(stat, s_work, ST_READY);
                 } else {
@@ -453,10 +459,12 @@ namespace {
 typedef void (*PersistFn)(DSceneView, DCamera, DRenderParams, PsCounters*, AccumFx*, unsigned long long*, unsigned int, unsigned long long*, PsTune);
 struct Variant {
     int layout, smem_stack, threads, scene;
-    PersistFn fn, fn_stats;
+    PersistFn fn, fn_general, fn_stats;  // fn: scenes with <= 4 single-primitive media; fn_general: any media (rt_device.cuh: sample_media)
     const char* name;
 };
-#define PS_INSTANCE(wide, sd, nt, scene) persist_kernel<false, wide, sd, nt, scene>, persist_kernel<true, wide, sd, nt, scene>
+// [fast-media instance, general-media instance, stats instance (decides at run time)]
+#define PS_INSTANCE(wide, sd, nt, scene) \
+    persist_kernel<false, wide, sd, nt, scene, MEDIA_FAST>, persist_kernel<false, wide, sd, nt, scene, MEDIA_GENERAL>, persist_kernel<true, wide, sd, nt, scene, MEDIA_ANY>
 // The kernel instances the library carries.  Measured on C4 (profiles/r2_ab_variants.txt): [1] is +1.6 % over [0], [2]
 // (one 768-thread block per SM instead of six 128-thread blocks: 5 KB more L1, one pool) another +1.8 %.
 // RTB_PS_EXPERIMENTS adds the rejected placements (stack levels or scene copies in shared memory: -2 ... -9 %, the L1
@@ -515,10 +523,11 @@ int launch_persist(RtScene* s, const DCamera& cam, const RtParams* p, int begin,
     const Variant& V = kVariants[vi];
     const size_t smem = variant_smem(V, s);
     const int NT = V.threads;
+    const PersistFn kernel = s->view.media_general ? V.fn_general : V.fn;
     if (w->blocks[vi] == 0) {
         int per_sm = 0, sms = 0;
-        for (PersistFn f : {V.fn, V.fn_stats}) CU_TRY(cudaFuncSetAttribute(f, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        CU_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, V.fn, NT, smem));
+        for (PersistFn f : {kernel, V.fn_stats}) CU_TRY(cudaFuncSetAttribute(f, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        CU_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kernel, NT, smem));
         if (per_sm < 1) return set_error(RT_ERR_CUDA, "persistent pipeline: kernel instance '%s' does not fit an SM", V.name);
         if (const char* e = getenv("RT_PS_BLOCKS_PER_SM")) per_sm = std::min(per_sm, std::max(1, atoi(e)));
         // Ask for exactly the shared memory the resident blocks need (+1 KB per block the runtime reserves); whatever is left
@@ -527,7 +536,7 @@ int launch_persist(RtScene* s, const DCamera& cam, const RtParams* p, int begin,
         int need_kb = (int)((per_sm * (smem + 1024) + 1023) / 1024);
         int percent = std::min(100, (need_kb * 100 + 227) / 228);
         if (const char* e = getenv("RT_PS_CARVEOUT")) percent = atoi(e);
-        CU_TRY(cudaFuncSetAttribute(V.fn, cudaFuncAttributePreferredSharedMemoryCarveout, percent));
+        CU_TRY(cudaFuncSetAttribute(kernel, cudaFuncAttributePreferredSharedMemoryCarveout, percent));
         CU_TRY(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, s->device));
         w->blocks[vi] = per_sm * std::max(1, sms);  // persistent: exactly what is co-resident
     }
@@ -566,7 +575,7 @@ int launch_persist(RtScene* s, const DCamera& cam, const RtParams* p, int begin,
             for (int k = 0; k < PSS_COUNT; ++k) fprintf(stderr, " %s=%llu", names[k], h[k]);
             fprintf(stderr, "\n");
         } else {
-            V.fn<<<blocks, NT, smem, stream>>>(s->view, cam, P, w->ctr, d_accum, s->d_rays, chunk, nullptr, tune);
+            kernel<<<blocks, NT, smem, stream>>>(s->view, cam, P, w->ctr, d_accum, s->d_rays, chunk, nullptr, tune);
         }
         CU_TRY(cudaGetLastError());
         *launches += 2;

@@ -149,6 +149,7 @@ struct DSceneView {
     const unsigned short* perlin_perm;  // n_perlin x 3 x 1024
     const DImage* images;
     int32_t n_nodes, n_nodes4, n_prims, n_media, n_perlin;
+    int32_t media_general;  // more than four media, or a boundary of several primitives: the out-of-line sampler
     int32_t bg_kind;
     float bg_top[3];
     float bg_bottom[3];

@@ -173,6 +173,7 @@ class Renderer:  # raytrace.rs:137-198
         self.parameters, self.tracer, self.rng = parameters, tracer, rng
         self.stats = None
         self.pipeline = abi.RT_PIPELINE_AUTO
+        self.bvh_layout = 0  # 0 = auto, 2 = binary 32-byte-node BVH, 4 = 4-wide BVH (RtParams.bvh_layout)
 
     @classmethod
     def new_with_rng(cls, camera, world, background, parameters, tracer, rng):
@@ -183,7 +184,7 @@ class Renderer:  # raytrace.rs:137-198
         p.width, p.height = self.parameters.image_width, self.parameters.image_height
         p.samples_per_pixel, p.max_depth = self.parameters.samples_per_pixel, self.tracer.max_depth
         p.seed, p.sample_begin, p.sample_count = self.rng.seed, 0, 0
-        p.pipeline, p.device = self.pipeline, -1
+        p.pipeline, p.device, p.bvh_layout = self.pipeline, -1, self.bvh_layout
         return p
 
     def render_arrays(self, logger=None, want_accum=True):
@@ -200,7 +201,8 @@ class Renderer:  # raytrace.rs:137-198
                                        accum.ctypes.data_as(C.c_void_p) if want_accum else None,
                                        rgb.ctypes.data_as(C.c_void_p), cb, None, C.byref(stats)))
         self.stats = {"paths": stats.paths, "rays": stats.rays, "device_ms": stats.device_ms,
-                      "kernel_launches": stats.kernel_launches, "pipeline": stats.pipeline_used}
+                      "kernel_launches": stats.kernel_launches, "pipeline": stats.pipeline_used,
+                      "bvh_layout": stats.bvh_layout_used}
         return rgb, accum
 
     def render(self, logger=None):

@@ -182,6 +182,36 @@ int32_t orc_medium_interval_batch(void* h, int32_t node, const double* rays, int
     return 0;
 }
 
+// Material::scatter / emit (materials.rs:7-11, :25-127; volumes.rs:77-83) of description material `material` for a batch
+// of caller-supplied hits.  in: n x 15 doubles (ray origin, ray dir, p, normal, u, v, front_face); item i draws from
+// Pcg64::seed_from_u64(seed_base + i).  out: n x 11 doubles (scattered, attenuation rgb, direction xyz, emitted rgb, the
+// first unit() of that stream — what a Dielectric compares its reflectance with, materials.rs:98).
+int32_t orc_scatter_batch(void* h, int32_t material, const double* in, int64_t n, uint64_t seed_base, double* out) {
+    OrcWorld* W = (OrcWorld*)h;
+    if (!W->from_desc || material < 0 || material >= (int32_t)W->mats.size()) return -1;
+    MaterialPtr m = material_from_desc(W->foreign, material, W->mats, W->texs);
+    if (!m) return -1;
+    for (int64_t i = 0; i < n; i++) {
+        const double* q = in + 15 * i;
+        double* o = out + 11 * i;
+        Ray ray{Point3(q[0], q[1], q[2]), Vec3(q[3], q[4], q[5])};
+        Hit hit;
+        hit.p = Point3(q[6], q[7], q[8]), hit.normal = Vec3(q[9], q[10], q[11]);
+        hit.u = q[12], hit.v = q[13], hit.front_face = q[14] != 0.0, hit.material = m.get();
+        Ctx cx;
+        cx.rng = Pcg64::seed_from_u64(seed_base + (uint64_t)i);
+        Pcg64 peek = cx.rng;
+        o[10] = peek.unit();
+        Color att(0, 0, 0);
+        Ray sc{hit.p, Vec3(0, 0, 0)};
+        bool alive = m->scatter(ray, hit, cx, att, sc);  // raytrace.rs:92-96: scatter, else emit
+        Color em = alive ? Color(0, 0, 0) : m->emit(hit.u, hit.v, hit.p, cx.c);
+        o[0] = alive ? 1.0 : 0.0;
+        for (int k = 0; k < 3; k++) o[1 + k] = alive ? att.e[k] : 0.0, o[4 + k] = alive ? sc.dir.e[k] : 0.0, o[7 + k] = em.e[k];
+    }
+    return 0;
+}
+
 // ---- small probes used to pin the restatement against known answers ----
 void orc_pcg_seed_stream(uint64_t seed, int32_t n, uint64_t* out) {
     Pcg64 r = Pcg64::seed_from_u64(seed);

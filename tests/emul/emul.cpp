@@ -32,6 +32,8 @@ static void make_view(EmulScene& e) {
     v.perlin_vec = f.perlin_vec.data(), v.perlin_perm = f.perlin_perm.data(), v.images = e.images.data();
     v.n_nodes = (int)f.nodes.size(), v.n_prims = (int)f.prims.size(), v.n_media = (int)f.media.size();
     v.n_perlin = (int)(f.perlin_vec.size() / (4 * RTB_PERLIN_POINTS));
+    v.media_general = f.media.size() > 4 ? 1 : 0;
+    for (const auto& m : f.media) v.media_general |= m.count > 1 ? 1 : 0;
     v.bg_kind = f.bg_kind;
     for (int k = 0; k < 3; ++k) v.bg_top[k] = f.bg_top[k], v.bg_bottom[k] = f.bg_bottom[k];
 }
@@ -72,6 +74,11 @@ int32_t emul_prim_nodes(void* h, int32_t* out, int32_t cap) {
 void emul_intersect_batch(void* h, int32_t mode, const float* rays, int64_t n, RtHit* out) {
     EmulScene* e = (EmulScene*)h;
     for (int64_t i = 0; i < n; ++i) intersect_query(e->view, mode, rays + 8 * i, out[i]);
+}
+
+void emul_scatter_batch(void* h, const RtScatterIn* in, int64_t n, RtScatterOut* out) {
+    EmulScene* e = (EmulScene*)h;
+    for (int64_t i = 0; i < n; ++i) scatter_query(e->view, in[i], out[i]);
 }
 
 void emul_texture_value_batch(void* h, int32_t tex, const float* uvp, int64_t n, float* rgb) {

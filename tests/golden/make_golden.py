@@ -8,7 +8,11 @@ JSON this script writes).
    config worlds draw from it for seed 42.  Checked against upstream's published known answers before writing.
 2. published_render_probe.json — colours of the reference's own README renders (sample.jpg, final_scene.jpg) at
    the projected centres of scene objects: the only evidence about the reference's output that exists
-   independently of any restatement.
+   independently of any restatement; for final_scene.jpg the image box that the 1000 foam spheres
+   (the last objects the world RNG places) project into, from this file's own restatement of the recipe.
+3. published_final_scene.png, published_sample_blur.png — the decoded pixels of the reference's README renders
+   (final_scene.jpg, sample_blur.jpg; README.md:20-38 of the reference), stored losslessly: what the image-level
+   tests compare this repo's renders of the same command lines with.
 """
 import json
 import math
@@ -166,6 +170,27 @@ def camera_project(lookfrom, lookat, vfov, aspect, W, H, p):
     return s * (W - 1), (1 - t) * (H - 1), depth
 
 
+def foam_image_box(foam):
+    """image box (x0, x1, y0, y1; y from the top) of final_scene's foam: 1000 spheres of radius 10, rotate_y(15) then
+    translate(-100, 270, 395) (worlds.rs:455-465), seen by the (478,278,-600) -> (278,278,0), vfov 40 camera"""
+    th = math.radians(15.0)
+    c, s = math.cos(th), math.sin(th)
+    xs, ys = [], []
+    for x, y, z in foam:
+        p = [c * x + s * z - 100.0, y + 270.0, -s * x + c * z + 395.0]
+        px, py, depth = camera_project([478, 278, -600], [278, 278, 0], 40.0, 1.0, 800, 800, p)
+        r = 10.0 / depth / (2 * math.tan(math.radians(20.0))) * 799
+        xs += [px - r, px + r]
+        ys += [py - r, py + r]
+    return [int(min(xs)), int(max(xs)) + 1, int(min(ys)), int(max(ys)) + 1]
+
+
+def copy_published_renders():
+    from PIL import Image
+    for src, dst in (("final_scene.jpg", "published_final_scene.png"), ("sample_blur.jpg", "published_sample_blur.png")):
+        Image.open(os.path.join("/root/reference", src)).convert("RGB").save(os.path.join(HERE, dst), optimize=True)
+
+
 def probe_published_renders(spheres):
     from PIL import Image
     import numpy as np
@@ -235,6 +260,8 @@ def main():
     with open(os.path.join(HERE, "rng_golden.json"), "w") as f:
         json.dump(golden, f, indent=1)
     probes = probe_published_renders(spheres)
+    probes["final_scene_jpg"] = {"width": 800, "height": 800, "foam_box_x0_x1_y0_y1": foam_image_box(foam)}
+    copy_published_renders()
     with open(os.path.join(HERE, "published_render_probe.json"), "w") as f:
         json.dump(probes, f, indent=1)
     print("wrote rng_golden.json and published_render_probe.json;", len(probes["sample_jpg"]["probes"]), "probes")

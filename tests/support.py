@@ -60,6 +60,7 @@ def oracle():
         L.orc_camera_ray.argtypes = [C.POINTER(abi.RtCamera), C.c_double, C.c_double, C.c_uint64, C.c_void_p, C.c_void_p]
         L.orc_camera_basis.argtypes = [C.POINTER(abi.RtCamera), C.c_void_p]
         L.orc_texture_value.argtypes = [C.c_void_p, C.c_int32, C.c_void_p, C.c_int64, C.c_void_p]
+        L.orc_scatter_batch.argtypes = [C.c_void_p, C.c_int32, C.c_void_p, C.c_int64, C.c_uint64, C.c_void_p]
         L.orc_hardware_threads.restype = C.c_int32
         _oracle = L
     return _oracle
@@ -85,6 +86,7 @@ def emul():
         L.emul_prim_nodes.argtypes = [C.c_void_p, C.c_void_p, C.c_int32]
         L.emul_intersect_batch.argtypes = [C.c_void_p, C.c_int32, C.c_void_p, C.c_int64, C.c_void_p]
         L.emul_texture_value_batch.argtypes = [C.c_void_p, C.c_int32, C.c_void_p, C.c_int64, C.c_void_p]
+        L.emul_scatter_batch.argtypes = [C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p]
         L.emul_generate_rays.argtypes = [C.POINTER(abi.RtCamera), C.POINTER(abi.RtParams), C.c_void_p, C.c_void_p,
                                          C.c_int64, C.c_void_p, C.c_void_p]
         L.emul_philox.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p]

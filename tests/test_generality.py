@@ -117,11 +117,53 @@ def test_skewed_bvh_stays_within_the_traversal_stack():
         assert np.allclose(g["t"][hit], lin["t"][hit], rtol=1e-6, atol=0)
 
 
+def checker_far_from_origin(run_texture, n):
+    """Checker (textures.rs:40-49) at |p| up to 1000, i.e. sin() of up to 5000 rad: the device's f32 product 5 * x is off
+    by at most half an ulp of 5000 (2.4e-4 rad), so a point may change side only inside that band around a zero of
+    one of the three sines — and nowhere else (an approximate hardware sine would be off by ~1e-3 rad out there)"""
+    b = S.DescBuilder()
+    tex = b.checker(b.solid(0.2, 0.3, 0.1), b.solid(0.9, 0.9, 0.9))
+    desc = b.finish(b.sphere((0, 0, 0), 1.0, b.lambertian(tex)))
+    rng = np.random.default_rng(31)
+    uvp = np.zeros((n, 5))
+    uvp[:, 2:5] = rng.uniform(-1000, 1000, (n, 3))
+    uvp = uvp.astype(np.float32).astype(np.float64)
+    got = run_texture(desc, tex, uvp)
+    want = oracle_texture(desc, tex, uvp)
+    bad = np.abs(got - want).max(axis=1) > 1e-6
+    band = np.abs(np.sin(5.0 * uvp[:, 2:5])).min(axis=1)
+    assert bad.mean() < 1e-3, bad.mean()
+    assert np.all(band[bad] < 5e-4), band[bad].max()
+
+
+def test_checker_far_from_origin_emulated():
+    def run(desc, tex, uvp):
+        es = S.EmulScene(desc)
+        got = np.zeros((len(uvp), 3), np.float32)
+        u32 = uvp.astype(np.float32)
+        S.emul().emul_texture_value_batch(es.h, tex, u32.ctypes.data, len(uvp), got.ctypes.data)
+        return got
+    checker_far_from_origin(run, 100_000)
+
+
 # ------------------------------------------------------------------ the same through the C ABI on the GPU
+@pytest.mark.gpu
+def test_checker_far_from_origin_on_device():
+    def run(desc, tex, uvp):
+        scene = rt.Scene(rt.SceneDescription(desc, owned=False))
+        got = np.zeros((len(uvp), 3), np.float32)
+        u32 = uvp.astype(np.float32)
+        abi.check(abi.load().rt_texture_value_batch(scene.handle, tex, u32.ctypes.data, len(uvp), got.ctypes.data))
+        scene.close()
+        return got
+    checker_far_from_origin(run, 1_000_000)
+
+
+
 @pytest.mark.gpu
 def test_nested_checker_matches_oracle_on_device():
     b, desc, tex = nested_checker_desc()
-    scene = rt.Scene(rt.SceneDescription(C.pointer(desc), owned=False))
+    scene = rt.Scene(rt.SceneDescription(desc, owned=False))
     uvp = texture_points(200_000)
     got = np.zeros((len(uvp), 3), np.float32)
     u32 = uvp.astype(np.float32)
@@ -135,7 +177,7 @@ def test_nested_checker_matches_oracle_on_device():
 @pytest.mark.parametrize("pipeline", [abi.RT_PIPELINE_PERSISTENT, abi.RT_PIPELINE_MEGAKERNEL, abi.RT_PIPELINE_WAVEFRONT])
 def test_more_than_four_media_on_device(pipeline):
     b, desc = many_media_desc(6)
-    scene = rt.Scene(rt.SceneDescription(C.pointer(desc), owned=False))
+    scene = rt.Scene(rt.SceneDescription(desc, owned=False))
     assert scene.info()["media"] == 6
     ow = S.OracleWorld(desc=desc)
     cam = S.make_camera((0, 12, -90), (0, 8, 0), 40.0, 2.0)
@@ -159,7 +201,7 @@ def test_more_than_four_media_on_device(pipeline):
 @pytest.mark.gpu
 def test_skewed_bvh_on_device():
     b, desc = concentric_spheres_desc(1000)
-    scene = rt.Scene(rt.SceneDescription(C.pointer(desc), owned=False))
+    scene = rt.Scene(rt.SceneDescription(desc, owned=False))
     ow = S.OracleWorld(desc=desc)
     rng = np.random.default_rng(2)
     rays = S.random_rays(200_000, rng, [-20, -20, -20], [20, 20, 20], target=[0, 0, 0], spread=[8, 8, 8])
