@@ -512,9 +512,15 @@ class Flattener {
                     link = (uint32_t)make4(kids[c], depth + 1);
                 }
             }
+            // centre and half-extent; the half-extent is rounded up so that [c - h, c + h] contains [lo, hi]
+            float ctr[3], half[3];
+            for (int a = 0; a < 3; ++a) {
+                ctr[a] = (float)(0.5 * ((double)box[a] + (double)box[3 + a]));
+                half[a] = round_up(std::max((double)box[3 + a] - (double)ctr[a], (double)ctr[a] - (double)box[a]));
+            }
             DNode4& dst = out.nodes4[me];  // looked up after the recursion, which reallocates out.nodes4
-            dst.xy[c][0] = box[0], dst.xy[c][1] = box[1], dst.xy[c][2] = box[3], dst.xy[c][3] = box[4];
-            dst.loz[c] = box[2], dst.hiz[c] = box[5];
+            dst.ch[c][0] = ctr[0], dst.ch[c][1] = ctr[1], dst.ch[c][2] = half[0], dst.ch[c][3] = half[1];
+            dst.cz[c] = ctr[2], dst.hz[c] = half[2];
             dst.link[c] = link;
         }
         return me;

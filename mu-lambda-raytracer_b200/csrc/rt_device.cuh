@@ -483,18 +483,20 @@ RTB_DEV void closest_hit(const DSceneView& S, const Ray& r, float tmin, float tm
 // down = conservative): a five-exchange network on the keys sorts the children, the nearest becomes the cursor and the
 // others are pushed farthest first — as 4-byte stack entries that still carry the distance for the pop-time cull.
 #define RTB_KEY_MISS 0xFFFFFFFFu
-RTB_DEV uint32_t child_key(const float4& xy, float loz, float hiz, uint32_t link, const NodeRay& q, float tmin, float tmax) {
+RTB_DEV uint32_t child_key(const float4& ch, float cz, float hz, uint32_t link, const NodeRay& q, float tmin, float tmax) {
+    // slab interval of an axis = t_centre -+ half * |1/d|: multiply-adds only (FMA pipe), no per-axis min/max (ALU pipe)
 #if defined(__CUDA_ARCH__) && !defined(RTB_HOST_EMULATION) && RTB_USE_FFMA2
-    const float2 ixy = make_float2(q.inv.x, q.inv.y), nxy = make_float2(q.noi.x, q.noi.y);
-    const float2 a2 = __ffma2_rn(make_float2(xy.x, xy.y), ixy, nxy), b2 = __ffma2_rn(make_float2(xy.z, xy.w), ixy, nxy);
-    const float ax = a2.x, ay = a2.y, bx = b2.x, by = b2.y;
+    const float2 c2 = __ffma2_rn(make_float2(ch.x, ch.y), make_float2(q.inv.x, q.inv.y), make_float2(q.noi.x, q.noi.y));
+    const float tcx = c2.x, tcy = c2.y;
 #else
-    float ax = fmaf(xy.x, q.inv.x, q.noi.x), bx = fmaf(xy.z, q.inv.x, q.noi.x);
-    float ay = fmaf(xy.y, q.inv.y, q.noi.y), by = fmaf(xy.w, q.inv.y, q.noi.y);
+    const float tcx = fmaf(ch.x, q.inv.x, q.noi.x), tcy = fmaf(ch.y, q.inv.y, q.noi.y);
 #endif
-    float az = fmaf(loz, q.inv.z, q.noi.z), bz = fmaf(hiz, q.inv.z, q.noi.z);
-    float tn = fmaxf(fmaxf(fminf(ax, bx), fminf(ay, by)), fmaxf(fminf(az, bz), tmin));
-    float tf = fminf(fminf(fmaxf(ax, bx), fmaxf(ay, by)), fminf(fmaxf(az, bz), tmax));
+    const float tcz = fmaf(cz, q.inv.z, q.noi.z);
+    const float ax = fabsf(q.inv.x), ay = fabsf(q.inv.y), az = fabsf(q.inv.z);
+    const float nx = fmaf(-ch.z, ax, tcx), ny = fmaf(-ch.w, ay, tcy), nz = fmaf(-hz, az, tcz);
+    const float fx = fmaf(ch.z, ax, tcx), fy = fmaf(ch.w, ay, tcy), fz = fmaf(hz, az, tcz);
+    float tn = fmaxf(fmaxf(nx, ny), fmaxf(nz, tmin));
+    float tf = fminf(fminf(fx, fy), fminf(fz, tmax));
     bool hit = tn <= fmaf(tf, 1.0000004f, q.pad);
     return hit ? ((as_uint(tn) & 0xFFFF0000u) | link) : RTB_KEY_MISS;  // an empty slot's link is all ones: MISS either way
 }

@@ -22,14 +22,17 @@ struct alignas(16) DNode {
 };
 
 // ---- 4-wide BVH node, 128 B (one cache line): the binary tree collapsed so that a ray takes half as many dependent
-// fetch steps and every step tests four independent boxes.  Child c: xy[c] = (lo.x, lo.y, hi.x, hi.y), loz[c], hiz[c].
+// fetch steps and every step tests four independent boxes.  Child boxes are stored as CENTRE and HALF-EXTENT:
+// child c: ch[c] = (centre.x, centre.y, half.x, half.y), cz[c], hz[c].  With t_c = c * (1/d) - o/d the slab interval of an
+// axis is t_c -+ h * |1/d|: three multiply-adds on the FMA pipe instead of two multiply-adds and a min/max pair on the
+// ALU pipe, which is the busiest pipe of the traversal (60 % in the round-2 capture).
 // link[c]: 16-bit child link in the low half — bit 15 clear = index of an inner DNode4, bit 15 set = ONE primitive
 // (index in the low 15 bits) — or RTB_LINK4_EMPTY (all ones) for an unused slot.  The upper half of a used link is
 // zero, so that (bits(t_entry) & 0xFFFF0000) | link is directly the 4-byte sort/stack key of rt_device.cuh.
 struct alignas(16) DNode4 {
-    float xy[4][4];
-    float loz[4];
-    float hiz[4];
+    float ch[4][4];
+    float cz[4];
+    float hz[4];
     uint32_t link[4];
     uint32_t pad[4];
 };
