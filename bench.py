@@ -183,6 +183,7 @@ def run_b200(args, wl):
     if world_size > 1:
         import torch.distributed as dist
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+        host_group = dist.new_group(backend="gloo")  # host-side waits that keep the GPUs free (an NCCL barrier spins a kernel on them)
     lib = abi.load()
     dev = torch.device("cuda", local_rank)
     W, H = wl["width"], wl["height"]
@@ -294,6 +295,7 @@ def run_b200(args, wl):
     # ---- the same job through the ONE-process host of the same scheme (rt_render_multi: what `rt_main --gpus N` calls)
     multi = None
     if dist is not None and args.multi_steps > 0:
+        barrier()
         if rank == 0:
             scenes = [scene] + [rt.Scene(desc, device=g) for g in range(world_size) if g != local_rank]
             arr = (C.c_void_p * len(scenes))(*[s.handle for s in scenes])
@@ -312,6 +314,7 @@ def run_b200(args, wl):
                      "checksum_matches": int(host_rgb2.sum()) == checksum}
             for s in scenes[1:]:
                 s.close()
+        dist.barrier(group=host_group)  # the other ranks wait here on the host: their GPUs belong to rank 0's threads meanwhile
         barrier()
 
     cpu, algo, algo_source = None, ALGO_FROZEN, "frozen (tests/golden/algo_work.py, BASELINE.md section 4)"
