@@ -20,6 +20,7 @@ CLI = os.path.join(HERE, "rt_main")
 # for that A/B (abi.py: RT_B200_LIB selects it).
 MATH = ["-ftz=true", "-prec-div=false", "-prec-sqrt=false"]
 FLAVORS = {"": MATH, "fast": ["--use_fast_math"], "precise": [],
+           "exp": MATH + ["-DRTB_PS_EXPERIMENTS"],  # + the rejected kernel placements of rt_persist.cu (tools/experiments/)
            "floatred": MATH + ["-DRTB_AB_FLOAT_RED"]}  # cost of the 64-bit fixed-point REDs against 32-bit float REDs
 FLAVOR = os.environ.get("RT_BUILD_FLAVOR", "")
 if FLAVOR:

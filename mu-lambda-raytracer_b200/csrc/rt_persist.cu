@@ -46,7 +46,7 @@ struct PsCounters {
     unsigned long long next_path, total_paths, rays;
 };
 
-#define PS_VARIANTS 8
+#define PS_VARIANTS 12
 #define PS_DEFAULT_LAYOUT 4    // RT_BVH_LAYOUT / RtParams.bvh_layout override
 #define PS_DEFAULT_VARIANT 2   // index into kVariants for the 4-wide layout; RT_PS_VARIANT overrides
 #define PS_MAX_SMEM (227u * 1024u)
@@ -475,6 +475,9 @@ const Variant kVariants[] = {
     {4, 0, 128, 0, PS_INSTANCE(true, 0, 128, 0), "bvh4, 6 x 128 threads per SM"},
     {4, 0, 768, 0, PS_INSTANCE(true, 0, 768, 0), "bvh4, 1 x 768 threads per SM"},
 #ifdef RTB_PS_EXPERIMENTS
+    {4, 0, 640, 0, PS_INSTANCE(true, 0, 640, 0), "bvh4, 1 x 640 threads per SM (96 registers)"},
+    {4, 0, 896, 0, PS_INSTANCE(true, 0, 896, 0), "bvh4, 1 x 896 threads per SM (72 registers)"},
+    {4, 0, 1024, 0, PS_INSTANCE(true, 0, 1024, 0), "bvh4, 1 x 1024 threads per SM (64 registers)"},
     {4, 8, 128, 0, PS_INSTANCE(true, 8, 128, 0), "bvh4, 6 x 128 threads, 8 stack levels in shared memory"},
     {4, 0, 768, 1, PS_INSTANCE(true, 0, 768, 1), "bvh4, 1 x 768 threads, nodes in shared memory"},
     {4, 0, 768, 2, PS_INSTANCE(true, 0, 768, 2), "bvh4, 1 x 768 threads, primitives in shared memory"},
