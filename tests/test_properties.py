@@ -99,7 +99,7 @@ def test_sample_ranges_add_up_at_full_c4_size():
     c, rays_c, paths_c = _render_range(scene, cam, W, H, 64, 0, 64, 42)
     assert paths_a + paths_b == paths_c == W * H * 64
     assert rays_a + rays_b == rays_c  # the same Philox streams -> the same paths, ray for ray
-    assert np.allclose(a + b, c, rtol=2e-5, atol=2e-5 * c.mean())
+    assert np.allclose(a + b, c, rtol=1e-6, atol=0)  # the sums are exact integers on the device; only the float conversion of each rounds
     # and another seed is another image
     d, _, _ = _render_range(scene, cam, W, H, 64, 0, 64, 43)
     assert not np.allclose(c, d, rtol=1e-2, atol=1e-2 * c.mean())

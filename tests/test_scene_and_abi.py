@@ -123,6 +123,9 @@ def test_no_device_means_error_not_fallback():
     px, sm = np.zeros(1, np.int32), np.zeros(1, np.int32)
     rays, us = np.zeros(6, np.float32), np.zeros(4, np.float32)
     assert lib.rt_generate_rays(C.byref(cam.c), C.byref(p), px.ctypes.data, sm.ctypes.data, 1, rays.ctypes.data, us.ctypes.data) == abi.RT_ERR_NO_DEVICE
+    assert lib.rt_measure_peaks(0, C.byref(abi.RtPeaks())) == abi.RT_ERR_NO_DEVICE
+    assert lib.rt_tonemap_fixed_device(1, 1, 1, 1, 0, None) == abi.RT_ERR_NO_DEVICE
+    lib.rt_release_cached_memory()  # nothing cached, no device: a no-op
 
 
 def test_bad_arguments_are_rejected():
