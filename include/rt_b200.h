@@ -29,7 +29,7 @@
 extern "C" {
 #endif
 
-#define RT_B200_ABI_VERSION 2
+#define RT_B200_ABI_VERSION 3
 
 /* ---- status codes (replace the reference's unwrap()/panic!()) ---- */
 enum {
@@ -53,7 +53,11 @@ enum {
     RT_NODE_ROTATE = 7,    /* transforms.rs:51-142 axis = 0/1/2, f[0] = angle in degrees; child */
     RT_NODE_MEDIUM = 8,    /* volumes.rs:7-65      f[0] = density d; material = its Isotropic; child = boundary */
     RT_NODE_BVH = 9,       /* bhv.rs:85-101        children[first_child .. +child_count], insertion order */
-    RT_NODE_LIST = 10      /* hittable.rs:37-68    children[first_child .. +child_count], insertion order */
+    RT_NODE_LIST = 10,     /* hittable.rs:37-68    children[first_child .. +child_count], insertion order */
+    /* EXTENSION — no counterpart in the reference (src/vec.rs:215-219: its Ray has no time).  The MovingSphere of "Ray
+     * Tracing: The Next Week": f = c0x,c0y,c0z, c1x,c1y,c1z, radius; centre(time) = c0 + time * (c1 - c0) for the ray's
+     * time in [0, 1] (RtCamera.time0/time1).  Parity is stated against the oracle's restatement of the BOOK. */
+    RT_NODE_MOVING_SPHERE = 11
 };
 
 typedef struct RtNode {
@@ -135,6 +139,10 @@ typedef struct RtCamera {
     double aspect_ratio; /* the FLAG ratio, not W/H (main.rs:197) */
     double aperture;
     double focus_dist;
+    /* EXTENSION (motion blur; the reference's camera has no shutter): every camera ray — and the whole path after it —
+     * gets a time uniform in [time0, time1) within [0, 1], at which moving spheres are evaluated (resolution 2^-13).
+     * time0 = time1 = 0 is the reference's behaviour. */
+    double time0, time1;
 } RtCamera;
 
 /*
@@ -277,6 +285,8 @@ void rt_sample_slice(int32_t sample_begin, int32_t sample_count, int32_t n_parts
  *   rays: N x 8 floats: origin xyz, direction xyz (NOT normalised), t_min, t_max.
  */
 int rt_intersect_batch(const RtScene* scene, int32_t node, const float* rays, int64_t n, RtHit* out);
+/* the same with the rays at time `time` in [0, 1] (moving spheres; rt_intersect_batch is time 0) */
+int rt_intersect_batch_at(const RtScene* scene, int32_t node, float time, const float* rays, int64_t n, RtHit* out);
 
 /*
  * Material::scatter / Material::emit (materials.rs:7-11; impls :25-127, volumes.rs:77-83) for a batch of fixed hits

@@ -1,4 +1,4 @@
-//! FFI over include/rt_b200.h (ABI version 2): the GPU replacement of `Renderer::new_with_rng(..).render(..)`
+//! FFI over include/rt_b200.h (ABI version 3): the GPU replacement of `Renderer::new_with_rng(..).render(..)`
 //! (src/raytrace.rs:151-186), plus `SceneSink`, the recorder a Rust host fills while it builds a world.
 //!
 //! NOT compiled in this repository (there is no Rust toolchain in the build image or on the GPU box); kept in step
@@ -18,6 +18,7 @@ pub const RT_NODE_ROTATE: i32 = 7;
 pub const RT_NODE_MEDIUM: i32 = 8;
 pub const RT_NODE_BVH: i32 = 9;
 pub const RT_NODE_LIST: i32 = 10;
+pub const RT_NODE_MOVING_SPHERE: i32 = 11; // extension of the library (The Next Week's MovingSphere); the reference has none
 pub const RT_MAT_LAMBERTIAN: i32 = 1;
 pub const RT_MAT_METAL: i32 = 2;
 pub const RT_MAT_DIELECTRIC: i32 = 3;
@@ -104,6 +105,9 @@ pub struct RtCamera {
     pub aspect_ratio: f64,
     pub aperture: f64,
     pub focus_dist: f64,
+    /// shutter interval of the library's motion-blur extension; 0.0, 0.0 = the reference's camera
+    pub time0: f64,
+    pub time1: f64,
 }
 #[repr(C)]
 pub struct RtParams {
@@ -362,7 +366,7 @@ extern "C" fn logger_trampoline(row: c_int, total: c_int, user: *mut c_void) {
 }
 
 fn render_desc(desc: *const RtSceneDesc, job: &mut GpuJob) -> Vec<Vec<(i32, i32, i32)>> {
-    assert_eq!(unsafe { rt_abi_version() }, 2, "librt_b200.so speaks another ABI version than src/gpu.rs");
+    assert_eq!(unsafe { rt_abi_version() }, 3, "librt_b200.so speaks another ABI version than src/gpu.rs");
     let gpus = job.gpus.max(1).min(unsafe { rt_device_count() }.max(1) as usize);
     let mut scenes: Vec<*mut RtScene> = vec![std::ptr::null_mut(); gpus];
     for (g, s) in scenes.iter_mut().enumerate() {

@@ -11,7 +11,7 @@ import os
 RT_OK, RT_ERR_INVALID, RT_ERR_NO_DEVICE, RT_ERR_CUDA, RT_ERR_UNSUPPORTED = 0, 1, 2, 3, 4
 
 RT_NODE_SPHERE, RT_NODE_XYRECT, RT_NODE_XZRECT, RT_NODE_YZRECT, RT_NODE_BLOCK = 1, 2, 3, 4, 5
-RT_NODE_TRANSLATE, RT_NODE_ROTATE, RT_NODE_MEDIUM, RT_NODE_BVH, RT_NODE_LIST = 6, 7, 8, 9, 10
+RT_NODE_TRANSLATE, RT_NODE_ROTATE, RT_NODE_MEDIUM, RT_NODE_BVH, RT_NODE_LIST, RT_NODE_MOVING_SPHERE = 6, 7, 8, 9, 10, 11
 RT_MAT_LAMBERTIAN, RT_MAT_METAL, RT_MAT_DIELECTRIC, RT_MAT_DIFFUSE_LIGHT, RT_MAT_ISOTROPIC = 1, 2, 3, 4, 5
 RT_TEX_SOLID, RT_TEX_CHECKER, RT_TEX_NOISE, RT_TEX_IMAGE = 1, 2, 3, 4
 RT_BG_BLACK, RT_BG_GRADIENT = 0, 1
@@ -56,7 +56,7 @@ class RtSceneDesc(C.Structure):
 class RtCamera(C.Structure):
     _fields_ = [("lookfrom", C.c_double * 3), ("lookat", C.c_double * 3), ("vup", C.c_double * 3),
                 ("vfov_deg", C.c_double), ("aspect_ratio", C.c_double), ("aperture", C.c_double),
-                ("focus_dist", C.c_double)]
+                ("focus_dist", C.c_double), ("time0", C.c_double), ("time1", C.c_double)]
 
 
 class RtParams(C.Structure):
@@ -122,6 +122,7 @@ PROTOTYPES = {
     "rt_accum_fixed_to_float_device": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int64, C.c_int, C.c_void_p]),
     "rt_release_cached_memory": (None, []),
     "rt_intersect_batch": (C.c_int, [C.c_void_p, C.c_int32, C.c_void_p, C.c_int64, C.POINTER(RtHit)]),
+    "rt_intersect_batch_at": (C.c_int, [C.c_void_p, C.c_int32, C.c_float, C.c_void_p, C.c_int64, C.POINTER(RtHit)]),
     "rt_scatter_batch": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p]),
     "rt_texture_value_batch": (C.c_int, [C.c_void_p, C.c_int32, C.c_void_p, C.c_int64, C.c_void_p]),
     "rt_generate_rays": (C.c_int, [C.POINTER(RtCamera), C.POINTER(RtParams), C.c_void_p, C.c_void_p, C.c_int64,

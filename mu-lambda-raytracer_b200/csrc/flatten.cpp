@@ -172,6 +172,29 @@ class Flattener {
             box.grow(a), box.grow(b);
             return true;
         }
+        if (n.kind == RT_NODE_MOVING_SPHERE) {  // EXTENSION: The Next Week's MovingSphere, time in [0, 1]
+            if (!valid_material(n.material)) return fail(RT_ERR_INVALID, "moving sphere without a material");
+            int inst = instance_of(chain);
+            double c0[3] = {n.f[0], n.f[1], n.f[2]}, c1[3] = {n.f[3], n.f[4], n.f[5]}, r = n.f[6];
+            if (inst) {
+                double w0[3], w1[3];
+                inst_R[inst - 1].apply(c0, w0), inst_R[inst - 1].apply(c1, w1);
+                for (int i = 0; i < 3; ++i) c0[i] = w0[i] + inst_T[inst - 1].v[i], c1[i] = w1[i] + inst_T[inst - 1].v[i];
+            }
+            p.meta = PRIM_SPHERE | PRIM_MOVING | ((uint32_t)inst << PRIM_INST_SHIFT);
+            for (int i = 0; i < 3; ++i) p.v[i] = (float)c0[i];
+            p.v[3] = (float)r;
+            uint32_t idx = (uint32_t)(out.moving.size() / 4);
+            std::memcpy(&p.v[4], &idx, 4);
+            for (int i = 0; i < 3; ++i) out.moving.push_back((float)(c1[i] - c0[i]));
+            out.moving.push_back(0.0f);
+            double ar = std::fabs(r) * (1.0 + 1e-6) + 1e-6;  // the f32 centre moves along a rounded displacement
+            for (const double* c : {c0, c1}) {
+                double a[3] = {c[0] - ar, c[1] - ar, c[2] - ar}, b[3] = {c[0] + ar, c[1] + ar, c[2] + ar};
+                box.grow(a), box.grow(b);
+            }
+            return true;
+        }
         double lo[3], hi[3];
         uint32_t rect_axis = 0;
         if (n.kind == RT_NODE_XYRECT || n.kind == RT_NODE_XZRECT || n.kind == RT_NODE_YZRECT) {
@@ -674,6 +697,7 @@ void make_camera(const RtCamera& in, DCamera& out) {
         out.u[i] = (float)u[i], out.v[i] = (float)v[i];
     }
     out.lens_radius = (float)(in.aperture / 2.0);
+    out.time0 = (float)std::min(std::max(in.time0, 0.0), 1.0), out.time1 = (float)std::min(std::max(in.time1, 0.0), 1.0);
 }
 
 }  // namespace rtb

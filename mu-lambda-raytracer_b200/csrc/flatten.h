@@ -14,6 +14,7 @@ struct FlatScene {
     std::vector<DPrim> prims;       // in BVH leaf order
     std::vector<int32_t> prim_node; // description node of each primitive
     std::vector<DBigSphere> big;
+    std::vector<float> moving;      // 4 floats per moving sphere: c1 - c0 (world space), pad
     std::vector<DInstance> inst;
     std::vector<DMaterial> mats;    // same indexing as the description
     std::vector<DTexture> texs;     // same indexing as the description

@@ -205,6 +205,7 @@ int main(int argc, char** argv) {
     long long spp = (int32_t)parse_int(opt["samples_per_pixel"], "samples_per_pixel");
     long long max_depth = (int32_t)parse_int(opt["max_depth"], "max_depth");
     RtCamera cam;
+    cam.time0 = cam.time1 = 0.0;  // the reference's camera has no shutter (motion blur is an extension of the library)
     memcpy(cam.lookfrom, info.lookfrom, sizeof cam.lookfrom);
     memcpy(cam.lookat, info.lookat, sizeof cam.lookat);
     if (opt.count("lookfrom")) parse_vector(opt["lookfrom"], cam.lookfrom, "lookfrom");

@@ -68,13 +68,13 @@ __global__ void fixed_to_float_kernel(const AccumFx* __restrict__ accum, float* 
     out[i] = add ? out[i] + v : v;
 }
 
-__global__ void intersect_kernel(DSceneView S, int mode, const float* __restrict__ rays, long long n, RtHit* __restrict__ out) {
+__global__ void intersect_kernel(DSceneView S, int mode, const float* __restrict__ rays, long long n, RtHit* __restrict__ out, float time) {
     long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
     float q[8];
     for (int k = 0; k < 8; ++k) q[k] = rays[8 * i + k];
     RtHit h;
-    intersect_query(S, mode, q, h);
+    intersect_query(S, mode, q, h, time);
     out[i] = h;
 }
 
@@ -150,6 +150,7 @@ int upload_scene(RtScene* s) {
     DMedium* media;
     DPrim* media_prims;
     float* pvec;
+    float* moving;
     unsigned short* pperm;
     int rc;
     if ((rc = upload(f.nodes, &nodes, s->owned, s->device_bytes))) return rc;
@@ -162,6 +163,7 @@ int upload_scene(RtScene* s) {
     if ((rc = upload(f.media, &media, s->owned, s->device_bytes))) return rc;
     if ((rc = upload(f.media_prims, &media_prims, s->owned, s->device_bytes))) return rc;
     if ((rc = upload(f.perlin_vec, &pvec, s->owned, s->device_bytes))) return rc;
+    if ((rc = upload(f.moving, &moving, s->owned, s->device_bytes))) return rc;
     if ((rc = upload(f.perlin_perm, &pperm, s->owned, s->device_bytes))) return rc;
     // image textures -> CUDA texture objects (RGBA8, point sampling, clamp, texel coordinates)
     std::vector<DImage> images;
@@ -189,7 +191,7 @@ int upload_scene(RtScene* s) {
     DImage* dimages;
     if ((rc = upload(images, &dimages, s->owned, s->device_bytes))) return rc;
     v.nodes = nodes, v.nodes4 = f.nodes4.empty() ? nullptr : nodes4, v.n_nodes4 = (int)f.nodes4.size(), v.prims = prims, v.big = big, v.inst = inst, v.mats = mats, v.texs = texs, v.media = media, v.media_prims = media_prims;
-    v.perlin_vec = pvec, v.perlin_perm = pperm, v.images = dimages;
+    v.perlin_vec = pvec, v.perlin_perm = pperm, v.images = dimages, v.moving = moving;
     v.n_nodes = (int)f.nodes.size(), v.n_prims = (int)f.prims.size(), v.n_media = (int)f.media.size();
     v.n_perlin = (int)(f.perlin_vec.size() / (4 * RTB_PERLIN_POINTS));
     v.media_general = f.media.size() > 4 ? 1 : 0;
@@ -540,6 +542,10 @@ int rt_render(const RtScene* scene_, const RtCamera* cam, const RtParams* params
 }
 
 int rt_intersect_batch(const RtScene* scene, int32_t node, const float* rays, int64_t n, RtHit* out) {
+    return rt_intersect_batch_at(scene, node, 0.0f, rays, n, out);
+}
+
+int rt_intersect_batch_at(const RtScene* scene, int32_t node, float time, const float* rays, int64_t n, RtHit* out) {
     if (!scene || !rays || !out || n < 0) return set_error(RT_ERR_INVALID, "rt_intersect_batch: bad argument");
     if (n == 0) return RT_OK;
     DeviceGuard g(scene->device);
@@ -568,7 +574,7 @@ int rt_intersect_batch(const RtScene* scene, int32_t node, const float* rays, in
             rc = set_error(RT_ERR_CUDA, "rt_intersect_batch: upload failed");
             break;
         }
-        intersect_kernel<<<(unsigned)((n + 127) / 128), 128>>>(target->view, mode, d_rays, n, d_out);
+        intersect_kernel<<<(unsigned)((n + 127) / 128), 128>>>(target->view, mode, d_rays, n, d_out, time);
         cudaError_t e = cudaDeviceSynchronize();
         if (e != cudaSuccess) {
             rc = set_error(RT_ERR_CUDA, "rt_intersect_batch: kernel failed: %s", cudaGetErrorString(e));

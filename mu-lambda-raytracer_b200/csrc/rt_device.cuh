@@ -200,6 +200,19 @@ RTB_DEV V3 sample_unit_ball(float u0, float u1, float u2) {
 }
 
 // ------------------------------------------------------------------ camera (camera.rs:40-48, raytrace.rs:191-192)
+#define WF_TIME_SHIFT 19
+#define WF_TIME_MASK 0xFFF80000u
+RTB_DEV float time_of_flags(uint32_t flags) { return (float)(flags >> WF_TIME_SHIFT) * (1.0f / 8191.0f); }
+RTB_DEV uint32_t flags_of_time(float time) { return (uint32_t)(fminf(fmaxf(time, 0.0f), 1.0f) * 8191.0f + 0.5f) << WF_TIME_SHIFT; }
+// EXTENSION: the ray time of camera path (pixel, sample), uniform in the shutter interval, as the upper flag bits; drawn from
+// block 1 of the path's draw 0 (block 0 is the pixel jitter and the lens sample), only when the camera has a shutter
+RTB_DEV uint32_t camera_time_flags(const DCamera& cam, const PathRng& g0) {
+    if (!(cam.time1 > cam.time0)) return flags_of_time(cam.time0);
+    float ut[4];
+    rng_block(g0, 1u, ut);
+    return flags_of_time(cam.time0 + ut[0] * (cam.time1 - cam.time0));
+}
+
 RTB_DEV Ray generate_camera_ray(const DCamera& cam, const DRenderParams& P, int px, int py, const float u[4]) {
     float s = ((float)px + u[0]) * P.inv_wm1;
     float t = ((float)py + u[1]) * P.inv_hm1;
@@ -239,6 +252,15 @@ RTB_DEV PrimRec load_prim(const DPrim* p) {  // an element of the 32-byte-aligne
 // loop, where ptxas 12.9 crashes on the 256-bit form
 RTB_DEV PrimRec load_prim16(const DPrim* p) { return prim_from(ld4(p), ld4(reinterpret_cast<const char*>(p) + 16)); }
 RTB_DEV int prim_instance(const PrimRec& p) { return (int)((p.meta >> PRIM_INST_SHIFT) & PRIM_INST_MASK); }
+
+// EXTENSION (RT_NODE_MOVING_SPHERE; the reference has no ray time): a path carries ONE time for all its segments, quantised
+// to 13 bits in the upper bits of its flags word; a moving sphere is its record with the centre advanced to that time.
+RTB_DEV void apply_motion(const DSceneView& S, PrimRec& p, float time) {
+    if (p.meta & PRIM_MOVING) {
+        const float4 dc = ld4(S.moving + 4 * as_uint(p.v4));
+        p.v0 = fmaf(time, dc.x, p.v0), p.v1 = fmaf(time, dc.y, p.v1), p.v2 = fmaf(time, dc.z, p.v2);
+    }
+}
 
 // Sphere::hit (shapes.rs:57-82).  `from_surface`: the ray starts on this very sphere, so one root is
 // analytically zero (the reference rejects it through t_min) and the other is -2*half_b/a.
@@ -434,7 +456,7 @@ RTB_DEV int stack_pop(const StackEntry* stack, int& sp, float t_best, float pad)
 // Closest surface hit with t in [tmin, +inf): replaces HittableList::hit + BHV::hit + the shapes.
 // origin_prim/origin_face identify the primitive the ray starts on (-1 for camera and medium rays).
 RTB_DEV void closest_hit(const DSceneView& S, const Ray& r, float tmin, float tmax, int origin_prim, int origin_face, float& t_best, int& prim_best,
-                         int& face_best) {
+                         int& face_best, float time = 0.0f) {
     t_best = tmax, prim_best = -1, face_best = 0;
     if (S.n_prims == 0) return;
     const NodeRay nr = node_ray(r);
@@ -447,6 +469,7 @@ RTB_DEV void closest_hit(const DSceneView& S, const Ray& r, float tmin, float tm
             int first = v & 0xFFFFFF, count = v >> 24;
             for (int i = first; i < first + count; ++i) {
                 PrimRec p = load_prim(S.prims + i);
+                apply_motion(S, p, time);
                 float t;
                 int face;
                 if (hit_prim(S, p, r, tmin, t_best, i == origin_prim, origin_face, t, face)) t_best = t, prim_best = i, face_best = face;
@@ -537,7 +560,7 @@ RTB_DEV uint32_t stack4_pop(const uint32_t* stack, int& sp, float t_best, float 
 
 // closest_hit over the 4-wide tree (t_min must be > 0: keys compare as unsigned integers)
 RTB_DEV void closest_hit4(const DSceneView& S, const Ray& r, float tmin, float tmax, int origin_prim, int origin_face, float& t_best, int& prim_best,
-                          int& face_best) {
+                          int& face_best, float time = 0.0f) {
     t_best = tmax, prim_best = -1, face_best = 0;
     if (S.n_prims == 0) return;
     const NodeRay nr = node_ray(r);
@@ -548,6 +571,7 @@ RTB_DEV void closest_hit4(const DSceneView& S, const Ray& r, float tmin, float t
         if (cur & RTB_LINK4_LEAF) {
             const int i = (int)(cur & 0x7FFFu);
             PrimRec p = load_prim(S.prims + i);
+            apply_motion(S, p, time);
             float t;
             int face;
             if (hit_prim(S, p, r, tmin, t_best, i == origin_prim, origin_face, t, face)) t_best = t, prim_best = i, face_best = face;
@@ -568,10 +592,11 @@ RTB_DEV void closest_hit4(const DSceneView& S, const Ray& r, float tmin, float t
 }
 
 // brute force over a primitive range (test entry point; also cross-checks the BVH)
-RTB_DEV void closest_hit_linear(const DSceneView& S, const Ray& r, float tmin, float tmax, float& t_best, int& prim_best, int& face_best) {
+RTB_DEV void closest_hit_linear(const DSceneView& S, const Ray& r, float tmin, float tmax, float& t_best, int& prim_best, int& face_best, float time = 0.0f) {
     t_best = tmax, prim_best = -1, face_best = 0;
     for (int i = 0; i < S.n_prims; ++i) {
         PrimRec p = load_prim(S.prims + i);
+        apply_motion(S, p, time);
         float t;
         int face;
         if (hit_prim(S, p, r, tmin, t_best, false, -1, t, face)) t_best = t, prim_best = i, face_best = face;
@@ -857,6 +882,7 @@ struct PathState {
     int origin_prim;  // primitive the ray starts on, -1 if none
     int origin_face;
     int depth;        // rays still allowed (raytrace.rs:87-89)
+    float time;       // EXTENSION: the path's time in [0, 1] (moving spheres); 0 without a shutter
 };
 
 RTB_DEV V3 background_color(const DSceneView& S, const Ray& r) {  // raytrace.rs:29-35, :44-48
@@ -934,6 +960,7 @@ RTB_DEV bool scatter_event(const DSceneView& S, int medium, int prim, int face, 
         prim = -1, face = 0;
     } else {
         PrimRec Pr = load_prim(S.prims + prim);
+        apply_motion(S, Pr, ps.time);
         mat_index = Pr.mat;
         int tex = (int)as_uint(ld4(S.mats + mat_index).y);
         bool want_uv = tex >= 0 && texture_needs_uv(S, tex);
@@ -961,7 +988,7 @@ RTB_DEV bool extend_and_shade(const DSceneView& S, PathState& ps, PathRng& rng, 
         sample_media(S, ps.ray, RTB_T_MIN, rng, t, medium);
     }
     int prim, face;
-    closest_hit(S, ps.ray, RTB_T_MIN, t, ps.origin_prim, ps.origin_face, t, prim, face);
+    closest_hit(S, ps.ray, RTB_T_MIN, t, ps.origin_prim, ps.origin_face, t, prim, face, ps.time);
     if (prim >= 0) medium = -1;
     rng.draw = 2u + 2u * (uint32_t)segment;
     if (prim < 0 && medium < 0) {
@@ -1011,7 +1038,7 @@ RTB_DEV void integrate_item(const DSceneView& S, const DCamera& cam, const DRend
     rng.k0 = P.seed_lo, rng.k1 = P.seed_hi;
     rng.sample = 0, rng.draw = 0;
     PathState ps;
-    ps.depth = 0, ps.origin_prim = -1, ps.origin_face = 0;
+    ps.depth = 0, ps.origin_prim = -1, ps.origin_face = 0, ps.time = 0.0f;
     ps.beta = v3(0.f, 0.f, 0.f);
     ps.ray.o = ps.ray.d = v3(0.f, 0.f, 0.f);
     AccumFx acc[3] = {0ull, 0ull, 0ull};
@@ -1022,6 +1049,7 @@ RTB_DEV void integrate_item(const DSceneView& S, const DCamera& cam, const DRend
             if (next == count) break;
             rng.sample = (uint32_t)(first + next), rng.draw = 0;
             next += 1;
+            ps.time = time_of_flags(camera_time_flags(cam, rng));
             float u[4];
             rng_next4(rng, u);
             ps.ray = generate_camera_ray(cam, P, px, py, u);
@@ -1090,11 +1118,12 @@ RTB_DEV void wf_init_path(const DSceneView& S, const DCamera& cam, const DRender
 RTB_DEV void wf_init_camera(const DCamera& cam, const DRenderParams& P, uint32_t pixel, uint32_t sample, WfSlot& s) {
     PathRng rng;
     rng.pixel = pixel, rng.sample = sample, rng.draw = 0, rng.k0 = P.seed_lo, rng.k1 = P.seed_hi;
+    const uint32_t time_bits = camera_time_flags(cam, rng);
     float u[4];
     rng_next4(rng, u);
     Ray r = generate_camera_ray(cam, P, (int)(pixel % (uint32_t)P.width), (int)(pixel / (uint32_t)P.width), u);
     s.A = f4(r.o.x, r.o.y, r.o.z, as_float(pixel));
-    s.B = f4(r.d.x, r.d.y, r.d.z, as_float((uint32_t)P.max_depth));
+    s.B = f4(r.d.x, r.d.y, r.d.z, as_float((uint32_t)P.max_depth | time_bits));
     s.C = f4(1.f, 1.f, 1.f, as_float(sample));
     s.D = f4(0.f, 0.f, as_float(0xFFFFFFFFu), 0.f);
 }
@@ -1133,6 +1162,7 @@ RTB_DEV bool wf_shade_core(const DSceneView& S, const DRenderParams& P, WfSlot& 
     ps.depth -= 1;  // this segment's ray has been traced
     segment_next = segment + 1;
     ps.origin_prim = -1, ps.origin_face = 0;
+    ps.time = time_of_flags(flags);
     int code = (int)as_uint(s.D.y);
     float t = s.D.x;
     if (code < 0) {
@@ -1156,7 +1186,7 @@ RTB_DEV bool wf_shade_core(const DSceneView& S, const DRenderParams& P, WfSlot& 
         return false;
     }
     s.A = f4(ps.ray.o.x, ps.ray.o.y, ps.ray.o.z, s.A.w);
-    s.B = f4(ps.ray.d.x, ps.ray.d.y, ps.ray.d.z, as_float((uint32_t)ps.depth | ((uint32_t)ps.origin_face << WF_FACE_SHIFT)));
+    s.B = f4(ps.ray.d.x, ps.ray.d.y, ps.ray.d.z, as_float((uint32_t)ps.depth | ((uint32_t)ps.origin_face << WF_FACE_SHIFT) | (flags & WF_TIME_MASK)));
     s.C = f4(ps.beta.x, ps.beta.y, ps.beta.z, s.C.w);
     s.D.z = as_float((uint32_t)ps.origin_prim);
     return true;
@@ -1173,7 +1203,7 @@ RTB_DEV bool wf_shade(const DSceneView& S, const DRenderParams& P, WfSlot& s, V3
 enum { QUERY_BVH = 0, QUERY_LINEAR = 1, QUERY_MEDIUM = 2, QUERY_BVH4 = 3 };
 
 // Hittable::hit for one ray given as 8 floats (origin, direction, t_min, t_max) -> RtHit
-RTB_DEV void intersect_query(const DSceneView& S, int mode, const float* q, RtHit& out) {
+RTB_DEV void intersect_query(const DSceneView& S, int mode, const float* q, RtHit& out, float time = 0.0f) {
     Ray r;
     r.o = v3(q[0], q[1], q[2]), r.d = v3(q[3], q[4], q[5]);
     float tmin = q[6], tmax = q[7];
@@ -1187,11 +1217,12 @@ RTB_DEV void intersect_query(const DSceneView& S, int mode, const float* q, RtHi
     }
     float t;
     int prim, face;
-    if (mode == QUERY_BVH4 && S.nodes4 && tmin > 0.0f) closest_hit4(S, r, tmin, tmax, -1, 0, t, prim, face);
-    else if (mode == QUERY_BVH || mode == QUERY_BVH4) closest_hit(S, r, tmin, tmax, -1, 0, t, prim, face);
-    else closest_hit_linear(S, r, tmin, tmax, t, prim, face);
+    if (mode == QUERY_BVH4 && S.nodes4 && tmin > 0.0f) closest_hit4(S, r, tmin, tmax, -1, 0, t, prim, face, time);
+    else if (mode == QUERY_BVH || mode == QUERY_BVH4) closest_hit(S, r, tmin, tmax, -1, 0, t, prim, face, time);
+    else closest_hit_linear(S, r, tmin, tmax, t, prim, face, time);
     if (prim < 0) return;
     PrimRec P = load_prim(S.prims + prim);
+    apply_motion(S, P, time);
     Surface s;
     surface_at(S, P, r, t, face, true, s);
     out.t = t, out.u = s.u, out.v = s.v, out.front_face = s.front ? 1 : 0, out.material = P.mat, out.prim = prim;

@@ -410,6 +410,7 @@ __global__ void __launch_bounds__(NT, (STATS || NT > 128) ? 1 : PS_MIN_BLOCKS) p
                     } else {
                         q = load_prim(S.prims + i);
                     }
+                    if (q.meta & PRIM_MOVING) apply_motion(S, q, time_of_flags(__float_as_uint(POOL(tslot, R_FLAGS))));  // EXTENSION
                     float t;
                     int face;
                     if (hit_prim(S, q, r, RTB_T_MIN, t_best, i == origin_prim, origin_face, t, face))

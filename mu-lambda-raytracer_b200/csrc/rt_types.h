@@ -46,6 +46,7 @@ enum { PRIM_SPHERE = 0, PRIM_BOX = 1 };
 enum {
     PRIM_KIND_MASK = 0x3,
     PRIM_BIG = 0x4,            // sphere evaluated in f64 (|r| >= BIG_SPHERE_RADIUS); v[4] = index into big[]
+    PRIM_MOVING = 0x8,         // EXTENSION (RT_NODE_MOVING_SPHERE): centre = v[0..2] + time * moving[v[4]].xyz; never PRIM_BIG
     PRIM_INST_SHIFT = 4,       // bits 4..15: instance index + 1 (0 = world space)
     PRIM_INST_MASK = 0xFFF,
     PRIM_RECT_SHIFT = 16,      // bits 16..17: plane axis + 1 of an XY/XZ/YZ rect stored as a flat box (0 = Block)
@@ -124,6 +125,7 @@ struct DCamera {  // camera.rs:3-12, computed on the host in f64 by Camera::new'
     float u[3];
     float v[3];
     float lens_radius;
+    float time0, time1;  // EXTENSION: shutter interval of the ray time (0, 0 = none)
 };
 
 #define RTB_PERLIN_POINTS 1024
@@ -151,6 +153,7 @@ struct DSceneView {
     const float* perlin_vec;          // n_perlin x 1024 x 4 floats (xyz, pad)
     const unsigned short* perlin_perm;  // n_perlin x 3 x 1024
     const DImage* images;
+    const float* moving;  // EXTENSION: n x 4 floats, c1 - c0 of every moving sphere
     int32_t n_nodes, n_nodes4, n_prims, n_media, n_perlin;
     int32_t media_general;  // more than four media, or a boundary of several primitives: the out-of-line sampler
     int32_t bg_kind;

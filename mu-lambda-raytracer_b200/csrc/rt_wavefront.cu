@@ -222,6 +222,7 @@ __global__ void __launch_bounds__(WF_EXT_THREADS) wf_extend_kernel(DSceneView S,
                     PrimRec p = load_prim(S.prims + i);
                     float t;
                     int face;
+                    apply_motion(S, p, time_of_flags(flags));  // EXTENSION: moving spheres
                     if (hit_prim(S, p, r, RTB_T_MIN, t_best, i == origin_prim, (int)((flags >> WF_FACE_SHIFT) & 7u), t, face))
                         t_best = t, prim_best = i, face_best = face, mat_best = p.mat;
                 }

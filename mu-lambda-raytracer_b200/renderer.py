@@ -72,12 +72,14 @@ class SeedableRngator:  # rngator.rs:17-31 — on the device the seed keys the P
 
 
 class Camera:  # camera.rs:15-38: the seven inputs; the basis is derived inside the library in f64
-    def __init__(self, lookfrom, lookat, vup, vfov, aspect_ratio, aperture, focus_dist):
+    def __init__(self, lookfrom, lookat, vup, vfov, aspect_ratio, aperture, focus_dist, time0=0.0, time1=0.0):
+        """time0/time1: shutter interval in [0, 1] of the motion-blur EXTENSION (the reference's camera has none: 0, 0)"""
         self.c = abi.RtCamera()
         for i in range(3):
             self.c.lookfrom[i], self.c.lookat[i], self.c.vup[i] = float(lookfrom[i]), float(lookat[i]), float(vup[i])
         self.c.vfov_deg, self.c.aspect_ratio = float(vfov), float(aspect_ratio)
         self.c.aperture, self.c.focus_dist = float(aperture), float(focus_dist)
+        self.c.time0, self.c.time1 = float(time0), float(time1)
 
 
 class SceneDescription:

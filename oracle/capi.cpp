@@ -114,6 +114,7 @@ double orc_render(void* h, const RtCamera* cam, int32_t width, int32_t height, i
     J.cam = Camera(Point3(cam->lookfrom[0], cam->lookfrom[1], cam->lookfrom[2]),
                    Point3(cam->lookat[0], cam->lookat[1], cam->lookat[2]), Vec3(cam->vup[0], cam->vup[1], cam->vup[2]),
                    cam->vfov_deg, cam->aspect_ratio, cam->aperture, cam->focus_dist);
+    J.cam.time0 = cam->time0, J.cam.time1 = cam->time1;
     J.width = width; J.height = height; J.spp = spp; J.max_depth = max_depth;
     J.render_seed = render_seed;
     J.row_begin = row_begin; J.row_end = row_end;
@@ -135,13 +136,18 @@ int32_t orc_hardware_threads() { return (int32_t)std::thread::hardware_concurren
 // Hittable::hit of the subtree at description node `node` (-1 = root) for N rays given as 8 f64 each:
 // origin, direction (not normalised), t_min, t_max.  Media draw their free-flight sample from
 // Pcg64::seed_from_u64(rng_seed + ray index).
+int32_t orc_hit_batch_at(void* h, int32_t node, double time, const double* rays, int64_t n, uint64_t rng_seed, int32_t skip_media, OrcHit* out);
 int32_t orc_hit_batch(void* h, int32_t node, const double* rays, int64_t n, uint64_t rng_seed, int32_t skip_media, OrcHit* out) {
+    return orc_hit_batch_at(h, node, 0.0, rays, n, rng_seed, skip_media, out);
+}
+// the same with the rays at time `time` (moving-sphere extension)
+int32_t orc_hit_batch_at(void* h, int32_t node, double time, const double* rays, int64_t n, uint64_t rng_seed, int32_t skip_media, OrcHit* out) {
     OrcWorld* W = (OrcWorld*)h;
     HittablePtr obj = W->node(node);
     if (!obj) return -1;
     for (int64_t i = 0; i < n; i++) {
         const double* r = rays + 8 * i;
-        Ray ray{Point3(r[0], r[1], r[2]), Vec3(r[3], r[4], r[5])};
+        Ray ray{Point3(r[0], r[1], r[2]), Vec3(r[3], r[4], r[5]), time};
         Ctx cx;
         cx.rng = Pcg64::seed_from_u64(rng_seed + (uint64_t)i);
         cx.skip_media = skip_media != 0;

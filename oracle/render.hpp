@@ -16,6 +16,7 @@ struct Camera {  // camera.rs:3-12
     Point3 origin, lower_left_corner;
     Vec3 horizontal, vertical, u, v;
     double lens_radius;
+    double time0 = 0.0, time1 = 0.0;  // EXTENSION (The Next Week's shutter); 0, 0 = the reference's camera, no extra draw
 
     Camera() : lens_radius(0) {}
     Camera(Point3 lookfrom, Point3 lookat, Vec3 vup, double vfov, double aspect_ratio, double aperture,
@@ -36,7 +37,8 @@ struct Camera {  // camera.rs:3-12
     Ray get_ray(double s, double t, Pcg64& rng) const {  // camera.rs:40-48 — the disk sample is always drawn
         Vec3 rd = lens_radius * random_in_unit_disk(rng);
         Vec3 offset = u * rd.x() + v * rd.y();
-        return Ray{origin + offset, lower_left_corner + s * horizontal + t * vertical - origin - offset};
+        double time = time1 > time0 ? rng.gen_range_f64(time0, time1) : time0;
+        return Ray{origin + offset, lower_left_corner + s * horizontal + t * vertical - origin - offset, time};
     }
 };
 

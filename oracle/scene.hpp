@@ -51,9 +51,11 @@ inline Vec3 operator/(const Vec3& a, double s) { return Vec3(a.e[0] / s, a.e[1] 
 typedef Vec3 Point3;
 typedef Vec3 Color;
 
-struct Ray {  // vec.rs:215-228 — no time, direction NOT normalised
+struct Ray {  // vec.rs:215-228 — direction NOT normalised.  The reference's Ray has no time; `time` exists only for the
+              // moving-sphere EXTENSION below (it stays 0 for everything the reference can express)
     Point3 orig;
     Vec3 dir;
+    double time = 0.0;
     Point3 at(double t) const { return orig + t * dir; }
 };
 
@@ -247,11 +249,11 @@ struct Material {
 struct Lambertian : Material {  // materials.rs:14-34
     std::shared_ptr<Texture> albedo;
     explicit Lambertian(std::shared_ptr<Texture> a) : albedo(a) { kind = 1; }
-    bool scatter(const Ray&, const Hit& h, Ctx& cx, Color& att, Ray& out) const override {
+    bool scatter(const Ray& ray, const Hit& h, Ctx& cx, Color& att, Ray& out) const override {
         Vec3 dir = h.normal + random_in_hemisphere(h.normal, cx.rng);
         if (dir.near_zero()) dir = h.normal;
         att = albedo->value(h.u, h.v, h.p, cx.c);
-        out = Ray{h.p, dir};
+        out = Ray{h.p, dir, ray.time};
         return true;
     }
 };
@@ -262,7 +264,7 @@ struct Metal : Material {  // materials.rs:36-61
     Metal(Color a, double f) : albedo(a), fuzz(f) { kind = 2; }
     bool scatter(const Ray& ray, const Hit& h, Ctx& cx, Color& att, Ray& out) const override {
         Vec3 reflected = reflect(ray.dir.unit(), h.normal);
-        out = Ray{h.p, reflected + fuzz * random_in_unit_sphere(cx.rng)};
+        out = Ray{h.p, reflected + fuzz * random_in_unit_sphere(cx.rng), ray.time};
         if (out.dir.dot(h.normal) > 0.0) {
             att = albedo;
             return true;
@@ -298,7 +300,7 @@ struct Dielectric : Material {  // materials.rs:70-106
         // `||` short-circuits: no draw on total internal reflection (materials.rs:98)
         Vec3 dir = (cannot_refract || reflectance(cos_theta, ratio) > cx.rng.unit()) ? reflect(ud, h.normal)
                                                                                       : refract(ud, h.normal, ratio);
-        out = Ray{h.p, dir};
+        out = Ray{h.p, dir, ray.time};
         return true;
     }
 };
@@ -311,8 +313,8 @@ struct DiffuseLight : Material {  // materials.rs:108-127 — emits from both fa
 struct Isotropic : Material {  // volumes.rs:67-83 — direction = raw in-ball point
     std::shared_ptr<Texture> albedo;
     explicit Isotropic(std::shared_ptr<Texture> a) : albedo(a) { kind = 5; }
-    bool scatter(const Ray&, const Hit& h, Ctx& cx, Color& att, Ray& out) const override {
-        out = Ray{h.p, random_in_unit_sphere(cx.rng)};
+    bool scatter(const Ray& ray, const Hit& h, Ctx& cx, Color& att, Ray& out) const override {
+        out = Ray{h.p, random_in_unit_sphere(cx.rng), ray.time};
         att = albedo->value(h.u, h.v, h.p, cx.c);
         return true;
     }
@@ -420,6 +422,25 @@ struct Sphere : Hittable {  // shapes.rs:26-90
     }
 };
 
+// ---- EXTENSION, not in the reference: the MovingSphere of "Ray Tracing: The Next Week" (section 2.2-2.5), restated so that
+// the device's RT_NODE_MOVING_SPHERE has something to be compared with.  centre(time) = c0 + time * (c1 - c0), time in
+// [0, 1]; the hit is Sphere::hit with that centre; the box surrounds both ends.
+struct MovingSphere : Hittable {
+    Point3 center0, center1;
+    double radius;
+    MaterialPtr material;
+    MovingSphere(Point3 c0, Point3 c1, double r, MaterialPtr m) : center0(c0), center1(c1), radius(r), material(m) {}
+    bool hit(const Ray& r, double t_min, double t_max, Ctx& cx, Hit& out) const override {
+        Sphere at_time(center0 + r.time * (center1 - center0), radius, material);
+        at_time.desc_node = desc_node;
+        return at_time.hit(r, t_min, t_max, cx, out);
+    }
+    AABB bounding_box() const override {
+        Vec3 rv(std::fabs(radius), std::fabs(radius), std::fabs(radius));
+        return AABB(center0 - rv, center0 + rv).surround(AABB(center1 - rv, center1 + rv));
+    }
+};
+
 // ---- src/aarects.rs ----
 struct AARect {
     int a0, a1, aplane;
@@ -507,7 +528,7 @@ struct Translate : Hittable {  // transforms.rs:20-49
     Translate(Vec3 o, HittablePtr h) : original(h), offset(o) {}
     bool hit(const Ray& r, double t_min, double t_max, Ctx& cx, Hit& out) const override {
         cx.c.xform++;
-        Ray moved{r.orig - offset, r.dir};
+        Ray moved{r.orig - offset, r.dir, r.time};
         Hit h;
         if (!original->hit(moved, t_min, t_max, cx, h)) return false;
         // face-forwarding re-applied to an already flipped normal: front_face ends up true (App. C 16)
@@ -567,7 +588,7 @@ struct Rotate : Hittable {  // transforms.rs:51-148
     }
     bool hit(const Ray& r, double t_min, double t_max, Ctx& cx, Hit& out) const override {  // transforms.rs:127-142
         cx.c.xform++;
-        Ray rr{rotate_back(r.orig), rotate_back(r.dir)};
+        Ray rr{rotate_back(r.orig), rotate_back(r.dir), r.time};
         Hit h;
         if (!original->hit(rr, t_min, t_max, cx, h)) return false;
         int32_t dn = h.desc_node;

@@ -490,6 +490,9 @@ inline HittablePtr tree_from_desc(const RtSceneDesc& d, int32_t node, Pcg64& rng
     HittablePtr r;
     switch (n.kind) {
         case RT_NODE_SPHERE: r = std::make_shared<Sphere>(Point3(f[0], f[1], f[2]), f[3], m); break;
+        case RT_NODE_MOVING_SPHERE:  // extension, see scene.hpp
+            r = std::make_shared<MovingSphere>(Point3(f[0], f[1], f[2]), Point3(f[3], f[4], f[5]), f[6], m);
+            break;
         case RT_NODE_XYRECT: r = std::make_shared<RectShape>(xy_rect(f[0], f[1], f[2], f[3], f[4]), m); break;
         case RT_NODE_XZRECT: r = std::make_shared<RectShape>(xz_rect(f[0], f[1], f[2], f[3], f[4]), m); break;
         case RT_NODE_YZRECT: r = std::make_shared<RectShape>(yz_rect(f[0], f[1], f[2], f[3], f[4]), m); break;

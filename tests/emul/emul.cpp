@@ -29,7 +29,7 @@ static void make_view(EmulScene& e) {
     DSceneView& v = e.view;
     v.nodes = f.nodes.data(), v.nodes4 = f.nodes4.empty() ? nullptr : f.nodes4.data(), v.n_nodes4 = (int)f.nodes4.size(), v.prims = f.prims.data(), v.big = f.big.data(), v.inst = f.inst.data();
     v.mats = f.mats.data(), v.texs = f.texs.data(), v.media = f.media.data(), v.media_prims = f.media_prims.data();
-    v.perlin_vec = f.perlin_vec.data(), v.perlin_perm = f.perlin_perm.data(), v.images = e.images.data();
+    v.perlin_vec = f.perlin_vec.data(), v.perlin_perm = f.perlin_perm.data(), v.images = e.images.data(), v.moving = f.moving.data();
     v.n_nodes = (int)f.nodes.size(), v.n_prims = (int)f.prims.size(), v.n_media = (int)f.media.size();
     v.n_perlin = (int)(f.perlin_vec.size() / (4 * RTB_PERLIN_POINTS));
     v.media_general = f.media.size() > 4 ? 1 : 0;
@@ -74,6 +74,10 @@ int32_t emul_prim_nodes(void* h, int32_t* out, int32_t cap) {
 void emul_intersect_batch(void* h, int32_t mode, const float* rays, int64_t n, RtHit* out) {
     EmulScene* e = (EmulScene*)h;
     for (int64_t i = 0; i < n; ++i) intersect_query(e->view, mode, rays + 8 * i, out[i]);
+}
+void emul_intersect_batch_at(void* h, int32_t mode, float time, const float* rays, int64_t n, RtHit* out) {
+    EmulScene* e = (EmulScene*)h;
+    for (int64_t i = 0; i < n; ++i) intersect_query(e->view, mode, rays + 8 * i, out[i], time);
 }
 
 void emul_scatter_batch(void* h, const RtScatterIn* in, int64_t n, RtScatterOut* out) {

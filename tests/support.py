@@ -45,6 +45,7 @@ def oracle():
         L.orc_render.argtypes = [C.c_void_p, C.POINTER(abi.RtCamera), C.c_int32, C.c_int32, C.c_int32, C.c_int32,
                                  C.c_uint64, C.c_int32, C.c_int32, C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p]
         L.orc_hit_batch.argtypes = [C.c_void_p, C.c_int32, C.c_void_p, C.c_int64, C.c_uint64, C.c_int32, C.c_void_p]
+        L.orc_hit_batch_at.argtypes = [C.c_void_p, C.c_int32, C.c_double, C.c_void_p, C.c_int64, C.c_uint64, C.c_int32, C.c_void_p]
         L.orc_medium_interval_batch.argtypes = [C.c_void_p, C.c_int32, C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p]
         L.orc_pcg_seed_stream.argtypes = [C.c_uint64, C.c_int32, C.c_void_p]
         L.orc_pcg_new_stream.argtypes = [C.c_uint64, C.c_uint64, C.c_uint64, C.c_uint64, C.c_int32, C.c_void_p]
@@ -85,6 +86,7 @@ def emul():
         L.emul_scene_info.argtypes = [C.c_void_p] + [C.POINTER(C.c_int32)] * 4
         L.emul_prim_nodes.argtypes = [C.c_void_p, C.c_void_p, C.c_int32]
         L.emul_intersect_batch.argtypes = [C.c_void_p, C.c_int32, C.c_void_p, C.c_int64, C.c_void_p]
+        L.emul_intersect_batch_at.argtypes = [C.c_void_p, C.c_int32, C.c_float, C.c_void_p, C.c_int64, C.c_void_p]
         L.emul_texture_value_batch.argtypes = [C.c_void_p, C.c_int32, C.c_void_p, C.c_int64, C.c_void_p]
         L.emul_scatter_batch.argtypes = [C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p]
         L.emul_generate_rays.argtypes = [C.POINTER(abi.RtCamera), C.POINTER(abi.RtParams), C.c_void_p, C.c_void_p,
@@ -135,10 +137,10 @@ class OracleWorld:
         L.orc_world_bvh_axes(self.h, which, out.ctypes.data, n)
         return out
 
-    def hit(self, rays, node=-1, rng_seed=7, skip_media=True):
+    def hit(self, rays, node=-1, rng_seed=7, skip_media=True, time=0.0):
         rays = np.ascontiguousarray(rays, dtype=np.float64)
         out = (OrcHit * len(rays))()
-        rc = oracle().orc_hit_batch(self.h, node, rays.ctypes.data, len(rays), rng_seed, 1 if skip_media else 0, out)
+        rc = oracle().orc_hit_batch_at(self.h, node, float(time), rays.ctypes.data, len(rays), rng_seed, 1 if skip_media else 0, out)
         assert rc == 0
         return np.ctypeslib.as_array(out)
 
@@ -175,10 +177,10 @@ COUNTER_NAMES = ["paths", "rays", "aabb", "sphere", "rect", "xform", "medium", "
                  "light", "isotropic", "perlin", "image", "background", "depth_exhausted"]
 
 
-def make_camera(lookfrom, lookat, vfov, aspect, aperture=0.0, focus_dist=None, vup=(0, 1, 0)):
+def make_camera(lookfrom, lookat, vfov, aspect, aperture=0.0, focus_dist=None, vup=(0, 1, 0), time0=0.0, time1=0.0):
     if focus_dist is None:  # main.rs:109-112
         focus_dist = float(np.linalg.norm(np.asarray(lookat, float) - np.asarray(lookfrom, float)))
-    return rt.Camera(lookfrom, lookat, vup, vfov, aspect, aperture, focus_dist)
+    return rt.Camera(lookfrom, lookat, vup, vfov, aspect, aperture, focus_dist, time0, time1)
 
 
 class EmulScene:
@@ -194,10 +196,10 @@ class EmulScene:
         self.prim_nodes = np.zeros(max(self.n_prims, 1), dtype=np.int32)
         L.emul_prim_nodes(self.h, self.prim_nodes.ctypes.data, self.n_prims)
 
-    def intersect(self, rays, mode=0):
+    def intersect(self, rays, mode=0, time=0.0):
         rays = np.ascontiguousarray(rays, dtype=np.float32)
         out = (abi.RtHit * len(rays))()
-        emul().emul_intersect_batch(self.h, mode, rays.ctypes.data, len(rays), out)
+        emul().emul_intersect_batch_at(self.h, mode, float(time), rays.ctypes.data, len(rays), out)
         a = np.ctypeslib.as_array(out).copy()
         ok = a["prim"] >= 0
         a["prim"][ok] = self.prim_nodes[a["prim"][ok]]
@@ -317,6 +319,9 @@ class DescBuilder:
 
     def sphere(self, c, r, mat):
         return self._node(abi.RT_NODE_SPHERE, mat, [c[0], c[1], c[2], r])
+
+    def moving_sphere(self, c0, c1, r, mat):  # extension: centre(time) = c0 + time * (c1 - c0)
+        return self._node(abi.RT_NODE_MOVING_SPHERE, mat, [c0[0], c0[1], c0[2], c1[0], c1[1], c1[2], r])
 
     def rect(self, kind, a0, a1, b0, b1, k, mat):
         return self._node(kind, mat, [a0, a1, b0, b1, k])

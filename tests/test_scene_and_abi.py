@@ -96,14 +96,14 @@ def test_library_exports_every_declared_symbol():
     lib = abi.load()
     for name in declared:
         assert hasattr(lib, name), f"librt_b200.so does not export {name}"
-    assert lib.rt_abi_version() == 2
+    assert lib.rt_abi_version() == 3
 
 
 def test_struct_sizes_match_header():
     # sizes the C compiler gives the header's structs (LP64): guards the ctypes mirror against drift
     assert C.sizeof(abi.RtNode) == 88 and C.sizeof(abi.RtMaterial) == 48 and C.sizeof(abi.RtTexture) == 48
     assert C.sizeof(abi.RtPerlin) == 1024 * 24 + 3 * 4096 and C.sizeof(abi.RtImage) == 16
-    assert C.sizeof(abi.RtCamera) == 104 and C.sizeof(abi.RtParams) == 48 and C.sizeof(abi.RtHit) == 48
+    assert C.sizeof(abi.RtCamera) == 120 and C.sizeof(abi.RtParams) == 48 and C.sizeof(abi.RtHit) == 48
     assert C.sizeof(abi.RtStats) == 40 and C.sizeof(abi.RtSceneDesc) == 128
 
 
