@@ -229,6 +229,14 @@ void rt_scene_destroy(RtScene* scene);
  */
 void rt_release_cached_memory(void);
 int rt_scene_info(const RtScene* scene, int32_t* n_prims, int32_t* n_bvh_nodes, int32_t* n_media, int64_t* device_bytes);
+/*
+ * How the scene's BVH was built.  Scenes of RT_GPU_BUILD_MIN primitives or more (environment RT_BVH_GPU_MIN overrides)
+ * get a linear BVH built ON THE GPU (Morton codes, radix sort, Karras' parallel hierarchy, bottom-up boxes; an extension:
+ * the reference builds on the host, src/bhv.rs:122-145); smaller ones the host's SAH sweep plus the 4-wide collapse.
+ *   built_on_device: 1 / 0;  build_ms: device time of the GPU build (0 for a host build);  depth: depth of the binary tree
+ */
+#define RT_GPU_BUILD_MIN 32768
+int rt_scene_build_info(const RtScene* scene, int32_t* built_on_device, float* build_ms, int32_t* depth);
 
 /*
  * Renderer::new_with_rng + render (raytrace.rs:151-186) with HOST buffers.

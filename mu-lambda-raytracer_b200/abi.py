@@ -108,6 +108,7 @@ PROTOTYPES = {
     "rt_scene_destroy": (None, [C.c_void_p]),
     "rt_scene_info": (C.c_int, [C.c_void_p, C.POINTER(C.c_int32), C.POINTER(C.c_int32), C.POINTER(C.c_int32),
                                 C.POINTER(C.c_int64)]),
+    "rt_scene_build_info": (C.c_int, [C.c_void_p, C.POINTER(C.c_int32), C.POINTER(C.c_float), C.POINTER(C.c_int32)]),
     "rt_render": (C.c_int, [C.c_void_p, C.POINTER(RtCamera), C.POINTER(RtParams), C.c_void_p, C.c_void_p,
                             RtProgressFn, C.c_void_p, C.POINTER(RtStats)]),
     "rt_render_accumulate_device": (C.c_int, [C.c_void_p, C.POINTER(RtCamera), C.POINTER(RtParams), C.c_void_p,

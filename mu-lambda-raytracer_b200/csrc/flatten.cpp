@@ -650,7 +650,7 @@ class Flattener {
 
 }  // namespace
 
-int flatten_scene(const RtSceneDesc* desc, int32_t root, bool build_bvh, FlatScene& out, std::string& err) {
+int flatten_scene(const RtSceneDesc* desc, int32_t root, int build, FlatScene& out, std::string& err) {
     if (!desc || desc->n_nodes <= 0 || !desc->nodes) {
         err = "empty scene description";
         return RT_ERR_INVALID;
@@ -664,7 +664,17 @@ int flatten_scene(const RtSceneDesc* desc, int32_t root, bool build_bvh, FlatSce
     std::vector<Wrapper> chain;
     f.walk(root, chain, 0);
     if (f.status != RT_OK) return f.status;
-    if (build_bvh) f.build_bvh();
+    size_t gpu_min = RTB_GPU_BUILD_MIN;
+    if (const char* e = getenv("RT_BVH_GPU_MIN")) gpu_min = (size_t)std::max(2, atoi(e));
+    const bool device_build = build == BUILD_AUTO && out.prims.size() >= gpu_min;
+    if (build != BUILD_NONE && !device_build) f.build_bvh();
+    if (f.status != RT_OK) return f.status;
+    out.needs_device_build = device_build;
+    out.prim_bounds.resize(6 * out.prims.size());
+    for (size_t i = 0; i < out.prims.size(); ++i) {  // after build_bvh the primitives are in leaf order: prims[i] <-> prim_box[order[i]]
+        const Box3& b = f.prim_box[f.order.empty() ? i : (size_t)f.order[i]];
+        for (int k = 0; k < 3; ++k) out.prim_bounds[6 * i + k] = round_down(b.lo[k]), out.prim_bounds[6 * i + 3 + k] = round_up(b.hi[k]);
+    }
     return f.status;
 }
 

@@ -32,12 +32,19 @@ struct FlatScene {
     float bg_top[3] = {0, 0, 0}, bg_bottom[3] = {0, 0, 0};
     int32_t bvh_depth = 0;
     int32_t bvh4_depth = 0;
+    std::vector<float> prim_bounds;    // 6 floats per primitive (world box, rounded outward), in `prims` order
+    bool needs_device_build = false;   // BUILD_AUTO left the BVH to the GPU builder (rt_lbvh.cu): `nodes` is still empty
+    bool built_on_device = false;
+    float device_build_ms = 0.0f;
 };
 
-// Flatten the subtree rooted at `root` (normally desc->root).  With build_bvh = false the primitives are
-// left in emission order and `nodes` stays empty (used by the brute-force test entry point).
-// Returns RT_OK or an RT_ERR_* code with `err` filled in.
-int flatten_scene(const RtSceneDesc* desc, int32_t root, bool build_bvh, FlatScene& out, std::string& err);
+// Flatten the subtree rooted at `root` (normally desc->root).  build: BUILD_NONE leaves the primitives in emission order
+// and `nodes` empty (the brute-force test entry point); BUILD_HOST = the SAH sweep + 4-wide collapse on the host;
+// BUILD_AUTO = the same for scenes below RTB_GPU_BUILD_MIN primitives (RT_BVH_GPU_MIN overrides), otherwise only
+// needs_device_build is set and the caller runs the GPU builder.  Returns RT_OK or an RT_ERR_* code with `err` filled in.
+enum { BUILD_NONE = 0, BUILD_HOST = 1, BUILD_AUTO = 2 };
+#define RTB_GPU_BUILD_MIN 32768  // above RTB_WIDE_MAX_PRIMS the 4-wide tree does not exist anyway
+int flatten_scene(const RtSceneDesc* desc, int32_t root, int build, FlatScene& out, std::string& err);
 
 // Camera::new (camera.rs:15-38) evaluated in f64, narrowed to the device record.
 void make_camera(const RtCamera& in, DCamera& out);

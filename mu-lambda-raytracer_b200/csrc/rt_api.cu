@@ -225,7 +225,7 @@ void free_scene(RtScene* s) {
 int create_scene(const RtSceneDesc* desc, int32_t root, bool build_bvh, int device, bool keep_desc, RtScene** out) {
     RtScene* s = new RtScene();
     std::string err;
-    int rc = flatten_scene(desc, root, build_bvh, s->flat, err);
+    int rc = flatten_scene(desc, root, build_bvh ? BUILD_AUTO : BUILD_NONE, s->flat, err);
     if (rc != RT_OK) {
         delete s;
         return set_error(rc, "%s", err.c_str());
@@ -233,6 +233,18 @@ int create_scene(const RtSceneDesc* desc, int32_t root, bool build_bvh, int devi
     if (device < 0) cudaGetDevice(&device);
     s->device = device;
     DeviceGuard g(device);
+    if (s->flat.needs_device_build) {  // large scene: linear BVH built on the GPU (rt_lbvh.cu); the host SAH sweep if that tree is too deep
+        rc = rtb::lbvh_build(s->flat, &s->flat.device_build_ms);
+        if (rc == RT_ERR_UNSUPPORTED) {
+            s->flat = FlatScene();
+            rc = flatten_scene(desc, root, BUILD_HOST, s->flat, err);
+            if (rc != RT_OK) set_error(rc, "%s", err.c_str());
+        }
+        if (rc != RT_OK) {
+            delete s;
+            return rc;
+        }
+    }
     rc = upload_scene(s);
     if (rc == RT_OK && rtb::cache_malloc((void**)&s->d_rays, sizeof(unsigned long long)) != cudaSuccess) rc = set_error(RT_ERR_CUDA, "cudaMalloc failed");
     if (rc == RT_OK && (cudaEventCreate(&s->ev0) != cudaSuccess || cudaEventCreate(&s->ev1) != cudaSuccess)) rc = set_error(RT_ERR_CUDA, "cudaEventCreate failed");
@@ -414,6 +426,14 @@ int rt_scene_info(const RtScene* scene, int32_t* n_prims, int32_t* n_bvh_nodes, 
     if (n_bvh_nodes) *n_bvh_nodes = (int32_t)scene->flat.nodes.size();
     if (n_media) *n_media = (int32_t)scene->flat.media.size();
     if (device_bytes) *device_bytes = scene->device_bytes;
+    return RT_OK;
+}
+
+int rt_scene_build_info(const RtScene* scene, int32_t* built_on_device, float* build_ms, int32_t* depth) {
+    if (!scene) return set_error(RT_ERR_INVALID, "rt_scene_build_info: null scene");
+    if (built_on_device) *built_on_device = scene->flat.built_on_device ? 1 : 0;
+    if (build_ms) *build_ms = scene->flat.device_build_ms;
+    if (depth) *depth = scene->flat.bvh_depth;
     return RT_OK;
 }
 

@@ -68,6 +68,7 @@ struct RtScene {
 };
 
 namespace rtb {
+int lbvh_build(FlatScene& f, float* build_ms);  // rt_lbvh.cu: BVH over f.prim_bounds on the current device
 int scene_scratch(RtScene* scene, size_t n_values);  // grow d_accum / d_accum_f / d_rgb to n_values
 // samples [begin, begin + count) of every pixel ADDED into the fixed-point buffer d_accum (memory of scene's device)
 int accumulate_fixed(const RtScene* scene, const RtCamera* cam, const RtParams* params, AccumFx* d_accum, cudaStream_t stream, RtProgressFn cb,

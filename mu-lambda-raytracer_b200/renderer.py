@@ -120,6 +120,11 @@ class Scene:
         abi.check(abi.load().rt_scene_info(self.handle, C.byref(a), C.byref(b), C.byref(c), C.byref(d)))
         return {"prims": a.value, "bvh_nodes": b.value, "media": c.value, "device_bytes": d.value}
 
+    def build_info(self):
+        a, b, c = C.c_int32(), C.c_float(), C.c_int32()
+        abi.check(abi.load().rt_scene_build_info(self.handle, C.byref(a), C.byref(b), C.byref(c)))
+        return {"built_on_device": bool(a.value), "build_ms": b.value, "depth": c.value}
+
     def close(self):
         if self.handle:
             abi.load().rt_scene_destroy(self.handle)

@@ -47,7 +47,7 @@ const char* emul_last_error() { return g_err.c_str(); }
 void* emul_scene_create(const RtSceneDesc* d, int32_t root, int32_t build_bvh) {
     EmulScene* e = new EmulScene();
     std::string err;
-    if (flatten_scene(d, root < 0 ? d->root : root, build_bvh != 0, e->flat, err) != RT_OK) {
+    if (flatten_scene(d, root < 0 ? d->root : root, build_bvh != 0 ? BUILD_HOST : BUILD_NONE, e->flat, err) != RT_OK) {
         g_err = err;
         delete e;
         return nullptr;
