@@ -530,7 +530,9 @@ int launch_persist(RtScene* s, const DCamera& cam, const RtParams* p, int begin,
     const PersistFn kernel = s->view.media_general ? V.fn_general : V.fn;
     if (w->blocks[vi] == 0) {
         int per_sm = 0, sms = 0;
-        for (PersistFn f : {kernel, V.fn_stats}) CU_TRY(cudaFuncSetAttribute(f, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        // (the statistics instance only when it will be launched: touching a kernel makes the driver load it, which a 3 ms job notices)
+        CU_TRY(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        if (getenv("RT_PS_STATS")) CU_TRY(cudaFuncSetAttribute(V.fn_stats, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         CU_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kernel, NT, smem));
         if (per_sm < 1) return set_error(RT_ERR_CUDA, "persistent pipeline: kernel instance '%s' does not fit an SM", V.name);
         if (const char* e = getenv("RT_PS_BLOCKS_PER_SM")) per_sm = std::min(per_sm, std::max(1, atoi(e)));
