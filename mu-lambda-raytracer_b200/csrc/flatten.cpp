@@ -267,7 +267,7 @@ class Flattener {
             }
             case RT_NODE_BVH:
             case RT_NODE_LIST: {
-                if (n.first_child < 0 || n.child_count < 0 || n.first_child + n.child_count > d->n_children)
+                if (n.first_child < 0 || n.child_count < 0 || (long long)n.first_child + n.child_count > (long long)d->n_children)
                     return fail(RT_ERR_INVALID, "list/bvh child range out of bounds");
                 for (int i = 0; i < n.child_count; ++i)
                     if (!collect_prims(d->children[n.first_child + i], chain, depth + 1, prims, boxes, nodes_out)) return false;
@@ -325,7 +325,7 @@ class Flattener {
             }
             case RT_NODE_BVH:
             case RT_NODE_LIST: {
-                if (n.first_child < 0 || n.child_count < 0 || n.first_child + n.child_count > d->n_children) {
+                if (n.first_child < 0 || n.child_count < 0 || (long long)n.first_child + n.child_count > (long long)d->n_children) {
                     fail(RT_ERR_INVALID, "list/bvh child range out of bounds");
                     return;
                 }
