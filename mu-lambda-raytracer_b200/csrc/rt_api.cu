@@ -253,6 +253,7 @@ int create_scene(const RtSceneDesc* desc, int32_t root, bool build_bvh, int devi
         return rc;
     }
     if (keep_desc) s->desc = rtb::clone_desc(desc);
+    if (build_bvh) rtb::persist_preload(s);
     *out = s;
     return RT_OK;
 }

@@ -513,6 +513,16 @@ int pick_variant(const RtScene* s, const RtParams* p) {
 
 int persist_layout_used(const RtScene* s, const RtParams* p) { return kVariants[pick_variant(s, p)].layout; }
 
+// Scene creation asks the driver for the kernel a default render of this scene will launch: CUDA loads kernel images
+// lazily, and for a job of a few milliseconds (C1 is 2 ms of work) that load would otherwise sit inside the first render.
+void persist_preload(const RtScene* s) {
+    RtParams p{};
+    p.max_depth = 1;
+    const Variant& V = kVariants[pick_variant(s, &p)];
+    cudaFuncAttributes fa;
+    if (cudaFuncGetAttributes(&fa, s->view.media_general ? V.fn_general : V.fn) != cudaSuccess) cudaGetLastError();
+}
+
 int launch_persist(RtScene* s, const DCamera& cam, const RtParams* p, int begin, int count, AccumFx* d_accum, cudaStream_t stream, RtProgressFn cb,
                    void* user, int* launches) {
     if (!persist_supports(s, p)) return set_error(RT_ERR_UNSUPPORTED, "persistent pipeline: max_depth above %d or more than 2^24 primitives", WF_DEPTH_MASK);

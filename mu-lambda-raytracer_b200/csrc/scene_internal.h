@@ -36,6 +36,7 @@ struct PersistState;    // rt_persist.cu
 
 DRenderParams device_params(const RtParams* p, int first_sample, int spi, int chunks);
 int persist_layout_used(const RtScene* s, const RtParams* p);
+void persist_preload(const RtScene* s);
 
 struct RowProgress {  // see rtb::row_progress (rt_api.cu)
     RtProgressFn cb;
