@@ -343,7 +343,8 @@ class Flattener {
                 }
                 // ConstantMedium's boundary is any Hittable (volumes.rs:7-11): every surface primitive below it
                 std::vector<DPrim> boundary;
-                if (!collect_prims(n.first_child, chain, depth + 1, boundary, nullptr, nullptr)) return;
+                std::vector<Box3> boundary_box;
+                if (!collect_prims(n.first_child, chain, depth + 1, boundary, &boundary_box, nullptr)) return;
                 if (boundary.empty()) return;  // an empty boundary is never hit: the medium does nothing
                 if (boundary.size() > 0xFFFF || out.media.size() >= RTB_MAX_MEDIA) {
                     fail(RT_ERR_UNSUPPORTED, "too many constant media / boundary primitives");
@@ -358,10 +359,78 @@ class Flattener {
                 out.media_prims.insert(out.media_prims.end(), boundary.begin(), boundary.end());
                 out.media.push_back(m);
                 out.media_node.push_back(node);
+                media_box.push_back(boundary_box[0]);
                 break;
             }
             default: collect_prims(node, chain, depth, out.prims, &prim_box, &out.prim_node);
         }
+    }
+
+    // ---- "clear" media: the interior of the boundary holds no surface.  A ray that starts inside such a medium and draws
+    // its next free-flight event inside it too cannot hit a surface first (the boundary is one convex primitive, so the
+    // whole segment stays inside), hence the persistent kernel advances such paths from event to event without a
+    // surface search (rt_persist.cu, chain phase).  Conservative test on the primitives as emitted (before the BVH build
+    // reorders them): a surface primitive disqualifies the medium when its world box reaches into the interior of the
+    // boundary's world box — for a spherical boundary: into the ball — unless it is a sphere around the same centre that
+    // is at least as large (the boundary itself, added as a glass shell: final_scene, worlds.rs:430-437).
+    std::vector<Box3> media_box;
+    void find_clear_media() {
+        out.clear_media = 0u;
+        for (size_t m = 0; m < out.media.size() && m < 32; ++m) {
+            const DMedium& M = out.media[m];
+            if (M.count != 1 || out.mats[M.mat].tex >= 0) continue;  // compound boundary / textured phase function: general path
+            const DPrim& B = M.boundary;
+            const bool ball = (B.meta & PRIM_KIND_MASK) == PRIM_SPHERE && !(B.meta & PRIM_MOVING);
+            if (!ball && (B.meta & PRIM_KIND_MASK) != PRIM_BOX) continue;
+            if (!ball && ((B.meta >> PRIM_RECT_SHIFT) & PRIM_RECT_MASK)) continue;  // a rect encloses nothing
+            const Box3& bb = media_box[m];
+            bool clear = true;
+            for (size_t i = 0; i < out.prims.size() && clear; ++i) {
+                const DPrim& q = out.prims[i];
+                const Box3& qb = prim_box[i];
+                bool reaches = true;
+                for (int k = 0; k < 3; ++k) reaches = reaches && qb.lo[k] < bb.hi[k] && qb.hi[k] > bb.lo[k];
+                if (!reaches) continue;
+                if (ball) {
+                    const double r = std::fabs((double)B.v[3]);
+                    double d2 = 0.0;  // squared distance from the centre to q's box
+                    for (int k = 0; k < 3; ++k) {
+                        const double c = (double)B.v[k], d = c < qb.lo[k] ? qb.lo[k] - c : (c > qb.hi[k] ? c - qb.hi[k] : 0.0);
+                        d2 += d * d;
+                    }
+                    if (d2 >= r * r) continue;
+                    const bool q_ball = (q.meta & PRIM_KIND_MASK) == PRIM_SPHERE && !(q.meta & PRIM_MOVING);
+                    if (q_ball && q.v[0] == B.v[0] && q.v[1] == B.v[1] && q.v[2] == B.v[2] && std::fabs(q.v[3]) >= std::fabs(B.v[3])) continue;
+                }
+                clear = false;
+            }
+            if (clear) out.clear_media |= 1u << m;
+        }
+        if (getenv("RT_NO_CLEAR_MEDIA")) out.clear_media = 0u;
+    }
+
+    // ---- F_* feature bits (rt_types.h): lets the persistent pipeline launch a kernel instance without the code this scene
+    // cannot reach.  Conservative: textures and materials count when the description holds them, used or not.
+    void find_features() {
+        uint32_t f = 0u;
+        auto prim_bits = [&](const DPrim& q, bool boundary) {
+            const bool sphere = (q.meta & PRIM_KIND_MASK) == PRIM_SPHERE;
+            const bool inst = ((q.meta >> PRIM_INST_SHIFT) & PRIM_INST_MASK) != 0;
+            if (q.meta & PRIM_BIG) f |= F_BIG;
+            if (q.meta & PRIM_MOVING) f |= F_MOVING;
+            if (boundary) {
+                if (!sphere) f |= F_BOXMEDIA;
+                return;
+            }
+            f |= sphere ? F_SPHERE : F_BOX;
+            if (!sphere && q.mat >= 0 && q.mat < (int)out.mats.size() && out.mats[q.mat].tex >= 0 && out.texs[out.mats[q.mat].tex].needs_uv) f |= F_UVBOX;
+            if (inst) f |= F_INSTANCE | (sphere ? 0u : F_INSTBOX);
+        };
+        for (const DPrim& q : out.prims) prim_bits(q, false);
+        for (const DPrim& q : out.media_prims) prim_bits(q, true);
+        if (!out.media.empty()) f |= F_MEDIA;
+        for (const DTexture& t : out.texs) f |= t.kind == TEX_CHECKER ? F_CHECKER : (t.kind == TEX_NOISE ? F_NOISE : (t.kind == TEX_IMAGE ? F_IMAGE : 0u));
+        out.features = f;
     }
 
     // ---- SAH BVH over prim_box ----
@@ -664,6 +733,8 @@ int flatten_scene(const RtSceneDesc* desc, int32_t root, int build, FlatScene& o
     std::vector<Wrapper> chain;
     f.walk(root, chain, 0);
     if (f.status != RT_OK) return f.status;
+    f.find_clear_media();
+    f.find_features();
     size_t gpu_min = RTB_GPU_BUILD_MIN;
     if (const char* e = getenv("RT_BVH_GPU_MIN")) gpu_min = (size_t)std::max(2, atoi(e));
     const bool device_build = build == BUILD_AUTO && out.prims.size() >= gpu_min;

@@ -21,6 +21,8 @@ struct FlatScene {
     std::vector<DMedium> media;
     std::vector<DPrim> media_prims;   // boundary primitives, medium after medium
     std::vector<int32_t> media_node;  // description node of each medium
+    uint32_t features = 0;            // F_* bits of rt_types.h: what the device code has to be able to handle for this scene
+    uint32_t clear_media = 0;         // bit m: the interior of medium m's boundary holds no surface (flatten.cpp: find_clear_media)
     std::vector<float> perlin_vec;           // n x 1024 x 4
     std::vector<unsigned short> perlin_perm; // n x 3 x 1024
     struct Image {

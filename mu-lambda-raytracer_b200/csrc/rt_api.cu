@@ -196,6 +196,7 @@ int upload_scene(RtScene* s) {
     v.n_perlin = (int)(f.perlin_vec.size() / (4 * RTB_PERLIN_POINTS));
     v.media_general = f.media.size() > 4 ? 1 : 0;
     for (const auto& m : f.media) v.media_general |= m.count > 1 ? 1 : 0;
+    v.clear_media = f.clear_media;
     v.bg_kind = f.bg_kind;
     for (int k = 0; k < 3; ++k) v.bg_top[k] = f.bg_top[k], v.bg_bottom[k] = f.bg_bottom[k];
     return RT_OK;
@@ -278,6 +279,7 @@ DRenderParams device_params(const RtParams* p, int first_sample, int spi, int ch
     P.tiles_x = (p->width + 7) / 8, P.tiles_y = (p->height + 3) / 4;
     P.seed_lo = (uint32_t)p->seed, P.seed_hi = (uint32_t)(p->seed >> 32);
     P.inv_wm1 = 1.0f / ((float)p->width - 1.0f), P.inv_hm1 = 1.0f / ((float)p->height - 1.0f);
+    P.inv_npix = 1.0 / ((double)p->width * (double)p->height);
     return P;
 }
 

@@ -149,12 +149,16 @@ struct Ray {
 };
 
 // ------------------------------------------------------------------ Philox4x32-10 (Salmon et al., SC'11)
-// Out of line on the device: three call sites per path segment (camera, media, scatter) share one copy of the
-// ten rounds, which keeps the instruction footprint of the shade stage inside the instruction cache.
+// Out of line on the device: three call sites per path segment (camera, media, scatter) share one copy of the ten
+// rounds AND of the conversion to uniforms, which keeps the instruction footprint of the shade stage inside the
+// instruction cache.
 struct U4 {
     uint32_t x, y, z, w;
 };
-RTB_DEV_NOINLINE U4 philox4x32_10v(uint32_t c0, uint32_t c1, uint32_t c2, uint32_t c3, uint32_t k0, uint32_t k1) {
+struct F4 {
+    float x, y, z, w;
+};
+RTB_DEV void philox_rounds(uint32_t& c0, uint32_t& c1, uint32_t& c2, uint32_t& c3, uint32_t k0, uint32_t k1) {
     const uint32_t M0 = 0xD2511F53u, M1 = 0xCD9E8D57u, W0 = 0x9E3779B9u, W1 = 0xBB67AE85u;
 #pragma unroll
     for (int round = 0; round < 10; ++round) {
@@ -164,11 +168,16 @@ RTB_DEV_NOINLINE U4 philox4x32_10v(uint32_t c0, uint32_t c1, uint32_t c2, uint32
         c0 = n0, c1 = lo1, c2 = n2, c3 = lo0;
         k0 += W0, k1 += W1;
     }
-    return U4{c0, c1, c2, c3};
 }
+// the raw block (known-answer tests)
 RTB_DEV void philox4x32_10(uint32_t c0, uint32_t c1, uint32_t c2, uint32_t c3, uint32_t k0, uint32_t k1, uint32_t out[4]) {
-    U4 r = philox4x32_10v(c0, c1, c2, c3, k0, k1);
-    out[0] = r.x, out[1] = r.y, out[2] = r.z, out[3] = r.w;
+    philox_rounds(c0, c1, c2, c3, k0, k1);
+    out[0] = c0, out[1] = c1, out[2] = c2, out[3] = c3;
+}
+// the block as four uniforms in [0, 1)
+RTB_DEV_NOINLINE F4 philox_uniforms(uint32_t c0, uint32_t c1, uint32_t c2, uint32_t c3, uint32_t k0, uint32_t k1) {
+    philox_rounds(c0, c1, c2, c3, k0, k1);
+    return F4{u32_to_unit(c0), u32_to_unit(c1), u32_to_unit(c2), u32_to_unit(c3)};
 }
 
 // one stream per camera path: counter = (pixel, sample, draw, tag), key = seed
@@ -179,9 +188,8 @@ struct PathRng {
 // block `block` of draw g.draw: four uniforms.  Block 0 is what rng_next4 returns; further blocks serve the media
 // beyond the fourth (sample_media).
 RTB_DEV void rng_block(const PathRng& g, uint32_t block, float u[4]) {
-    uint32_t r[4];
-    philox4x32_10(g.pixel, g.sample, g.draw, RTB_PHILOX_TAG + block, g.k0, g.k1, r);
-    u[0] = u32_to_unit(r[0]), u[1] = u32_to_unit(r[1]), u[2] = u32_to_unit(r[2]), u[3] = u32_to_unit(r[3]);
+    const F4 r = philox_uniforms(g.pixel, g.sample, g.draw, RTB_PHILOX_TAG + block, g.k0, g.k1);
+    u[0] = r.x, u[1] = r.y, u[2] = r.z, u[3] = r.w;
 }
 RTB_DEV void rng_next4(PathRng& g, float u[4]) {
     rng_block(g, 0u, u);
@@ -255,8 +263,9 @@ RTB_DEV int prim_instance(const PrimRec& p) { return (int)((p.meta >> PRIM_INST_
 
 // EXTENSION (RT_NODE_MOVING_SPHERE; the reference has no ray time): a path carries ONE time for all its segments, quantised
 // to 13 bits in the upper bits of its flags word; a moving sphere is its record with the centre advanced to that time.
-RTB_DEV void apply_motion(const DSceneView& S, PrimRec& p, float time) {
-    if (p.meta & PRIM_MOVING) {
+template <class SV>
+RTB_DEV void apply_motion(const SV& S, PrimRec& p, float time) {
+    if ((SV::feat & F_MOVING) && (p.meta & PRIM_MOVING)) {
         const float4 dc = ld4(S.moving + 4 * as_uint(p.v4));
         p.v0 = fmaf(time, dc.x, p.v0), p.v1 = fmaf(time, dc.y, p.v1), p.v2 = fmaf(time, dc.z, p.v2);
     }
@@ -282,17 +291,32 @@ RTB_DEV_NOINLINE Roots sphere_roots_f64(double cx, double cy, double cz, double 
     double disc = hb * hb - a * c;
     Roots out;
     out.real = !(disc < 0.0);
+#ifdef RTB_HOST_EMULATION
     double sq = sqrt(out.real ? disc : 0.0);
     out.t0 = (float)((-hb - sq) / a), out.t1 = (float)((-hb + sq) / a);
+#else
+    // 1/a and sqrt(disc) by two Newton steps from f32 seeds (relative error < 1e-12; the roots are narrowed to f32 anyway)
+    // instead of the IEEE division and square root, whose ~250 instructions of slow paths the instruction cache pays for
+    double ra = (double)(1.0f / (float)a);
+    ra = ra * (2.0 - a * ra), ra = ra * (2.0 - a * ra);  // 2^-22 -> 2^-44 -> 2^-88
+    double sq = 0.0;
+    if (out.real && disc > 1e-30) {
+        double y = (double)rsqrtf((float)disc);
+        y = y * (1.5 - 0.5 * disc * y * y), y = y * (1.5 - 0.5 * disc * y * y);
+        sq = disc * y;
+    }
+    out.t0 = (float)((-hb - sq) * ra), out.t1 = (float)((-hb + sq) * ra);
+#endif
     return out;
 }
 
 // both roots of the sphere quadratic, t0 <= t1 (shapes.rs:57-68); false when the discriminant is negative
-RTB_DEV bool sphere_roots(const DSceneView& S, const PrimRec& p, const Ray& r, float& t0, float& t1) {
+template <class SV>
+RTB_DEV bool sphere_roots(const SV& S, const PrimRec& p, const Ray& r, float& t0, float& t1) {
     V3 oc = r.o - v3(p.v0, p.v1, p.v2);
     float a = dot(r.d, r.d), hb = dot(oc, r.d), inv_a = 1.0f / a;
     float c = dot(oc, oc) - p.v3 * p.v3;
-    if (sphere_needs_f64(p, c)) {
+    if ((SV::feat & F_BIG) && sphere_needs_f64(p, c)) {
         const DBigSphere& b = S.big[as_uint(p.v4)];
         Roots q = sphere_roots_f64(b.c[0], b.c[1], b.c[2], b.r, r.o.x, r.o.y, r.o.z, r.d.x, r.d.y, r.d.z);
         t0 = q.t0, t1 = q.t1;
@@ -311,7 +335,8 @@ RTB_DEV bool sphere_roots(const DSceneView& S, const PrimRec& p, const Ray& r, f
 
 // Sphere::hit (shapes.rs:57-82).  `from_surface`: the ray starts on this very sphere, so one root is
 // analytically zero (the reference rejects it through t_min) and the other is -2*half_b/a.
-RTB_DEV bool hit_sphere(const DSceneView& S, const PrimRec& p, const Ray& r, float tmin, float tmax, bool from_surface, float& t_out) {
+template <class SV>
+RTB_DEV bool hit_sphere(const SV& S, const PrimRec& p, const Ray& r, float tmin, float tmax, bool from_surface, float& t_out) {
     float t0, t1;
     if (from_surface) {
         V3 oc = r.o - v3(p.v0, p.v1, p.v2);
@@ -331,12 +356,14 @@ RTB_DEV bool hit_sphere(const DSceneView& S, const PrimRec& p, const Ray& r, flo
 }
 
 // both crossings of a sphere boundary over (-inf, +inf): what ConstantMedium asks of its boundary
-RTB_DEV bool sphere_interval(const DSceneView& S, const PrimRec& p, const Ray& r, float& t0, float& t1) {
+template <class SV>
+RTB_DEV bool sphere_interval(const SV& S, const PrimRec& p, const Ray& r, float& t0, float& t1) {
     if (!sphere_roots(S, p, r, t0, t1)) return false;
     return t0 == t0 && t1 == t1;
 }
 
-RTB_DEV Ray to_object_space(const DSceneView& S, int inst, const Ray& r) {
+template <class SV>
+RTB_DEV Ray to_object_space(const SV& S, int inst, const Ray& r) {
     if (inst == 0) return r;
     const DInstance& I = S.inst[inst - 1];
     Ray o;
@@ -371,8 +398,9 @@ RTB_DEV bool box_slabs(const PrimRec& p, const Ray& r, int origin_face, float& t
 }
 
 // AARect::hit / Block::hit (aarects.rs:45-64, shapes.rs:188-191): closest side with t in [tmin, tmax]
-RTB_DEV bool hit_box(const DSceneView& S, const PrimRec& p, const Ray& r_world, float tmin, float tmax, int origin_face, float& t_out, int& face_out) {
-    Ray r = to_object_space(S, prim_instance(p), r_world);
+template <class SV>
+RTB_DEV bool hit_box(const SV& S, const PrimRec& p, const Ray& r_world, float tmin, float tmax, int origin_face, float& t_out, int& face_out) {
+    Ray r = (SV::feat & F_INSTBOX) ? to_object_space(S, prim_instance(p), r_world) : r_world;
     float te, tx;
     int fe, fx;
     if (!box_slabs(p, r, origin_face, te, tx, fe, fx)) return false;
@@ -393,8 +421,9 @@ RTB_DEV bool hit_box(const DSceneView& S, const PrimRec& p, const Ray& r_world, 
     return false;
 }
 
-RTB_DEV bool hit_prim(const DSceneView& S, const PrimRec& p, const Ray& r, float tmin, float tmax, bool is_origin, int origin_face, float& t, int& face) {
-    if ((p.meta & PRIM_KIND_MASK) == PRIM_SPHERE) {
+template <class SV>
+RTB_DEV bool hit_prim(const SV& S, const PrimRec& p, const Ray& r, float tmin, float tmax, bool is_origin, int origin_face, float& t, int& face) {
+    if (!(SV::feat & F_BOX) || ((SV::feat & F_SPHERE) && (p.meta & PRIM_KIND_MASK) == PRIM_SPHERE)) {
         face = 0;
         return hit_sphere(S, p, r, tmin, tmax, is_origin, t);
     }
@@ -455,7 +484,8 @@ RTB_DEV int stack_pop(const StackEntry* stack, int& sp, float t_best, float pad)
 
 // Closest surface hit with t in [tmin, +inf): replaces HittableList::hit + BHV::hit + the shapes.
 // origin_prim/origin_face identify the primitive the ray starts on (-1 for camera and medium rays).
-RTB_DEV void closest_hit(const DSceneView& S, const Ray& r, float tmin, float tmax, int origin_prim, int origin_face, float& t_best, int& prim_best,
+template <class SV>
+RTB_DEV void closest_hit(const SV& S, const Ray& r, float tmin, float tmax, int origin_prim, int origin_face, float& t_best, int& prim_best,
                          int& face_best, float time = 0.0f) {
     t_best = tmax, prim_best = -1, face_best = 0;
     if (S.n_prims == 0) return;
@@ -559,7 +589,8 @@ RTB_DEV uint32_t stack4_pop(const uint32_t* stack, int& sp, float t_best, float 
 }
 
 // closest_hit over the 4-wide tree (t_min must be > 0: keys compare as unsigned integers)
-RTB_DEV void closest_hit4(const DSceneView& S, const Ray& r, float tmin, float tmax, int origin_prim, int origin_face, float& t_best, int& prim_best,
+template <class SV>
+RTB_DEV void closest_hit4(const SV& S, const Ray& r, float tmin, float tmax, int origin_prim, int origin_face, float& t_best, int& prim_best,
                           int& face_best, float time = 0.0f) {
     t_best = tmax, prim_best = -1, face_best = 0;
     if (S.n_prims == 0) return;
@@ -592,7 +623,8 @@ RTB_DEV void closest_hit4(const DSceneView& S, const Ray& r, float tmin, float t
 }
 
 // brute force over a primitive range (test entry point; also cross-checks the BVH)
-RTB_DEV void closest_hit_linear(const DSceneView& S, const Ray& r, float tmin, float tmax, float& t_best, int& prim_best, int& face_best, float time = 0.0f) {
+template <class SV>
+RTB_DEV void closest_hit_linear(const SV& S, const Ray& r, float tmin, float tmax, float& t_best, int& prim_best, int& face_best, float time = 0.0f) {
     t_best = tmax, prim_best = -1, face_best = 0;
     for (int i = 0; i < S.n_prims; ++i) {
         PrimRec p = load_prim(S.prims + i);
@@ -605,8 +637,9 @@ RTB_DEV void closest_hit_linear(const DSceneView& S, const Ray& r, float tmin, f
 
 // ------------------------------------------------------------------ media (volumes.rs:25-65)
 // both crossings of one boundary primitive over (-inf, +inf), t0 <= t1 (a rect has one: t0 == t1)
-RTB_DEV bool boundary_crossings(const DSceneView& S, const PrimRec& b, const Ray& r, float& t0, float& t1) {
-    if ((b.meta & PRIM_KIND_MASK) == PRIM_SPHERE) return sphere_interval(S, b, r, t0, t1);
+template <class SV>
+RTB_DEV bool boundary_crossings(const SV& S, const PrimRec& b, const Ray& r, float& t0, float& t1) {
+    if (!(SV::feat & F_BOXMEDIA) || (b.meta & PRIM_KIND_MASK) == PRIM_SPHERE) return sphere_interval(S, b, r, t0, t1);
     Ray ro = to_object_space(S, prim_instance(b), r);
     int fe, fx;
     return box_slabs(b, ro, -1, t0, t1, fe, fx);
@@ -642,13 +675,15 @@ RTB_DEV bool clip_interval(float te, float tx, float tmin, float tmax, float& t1
     return true;
 }
 // single-primitive boundary (every shipped world): entry and exit of that primitive
-RTB_DEV bool medium_interval(const DSceneView& S, const PrimRec& b, const Ray& r, float tmin, float tmax, float& t1, float& t2) {
+template <class SV>
+RTB_DEV bool medium_interval(const SV& S, const PrimRec& b, const Ray& r, float tmin, float tmax, float& t1, float& t2) {
     float te, tx;
     if (!boundary_crossings(S, b, r, te, tx)) return false;
     if (!(tx >= te + 0.001f)) return false;  // second boundary.hit(h1.t + 0.001, inf) finds nothing
     return clip_interval(te, tx, tmin, tmax, t1, t2);
 }
-RTB_DEV bool medium_interval_any(const DSceneView& S, const DMedium* M, const Ray& r, float tmin, float tmax, float& t1, float& t2) {
+template <class SV>
+RTB_DEV bool medium_interval_any(const SV& S, const DMedium* M, const Ray& r, float tmin, float tmax, float& t1, float& t2) {
     if (M->count <= 1) return medium_interval(S, load_prim16(&M->boundary), r, tmin, tmax, t1, t2);
     const V3 h = compound_boundary(S, M->first, M->count, r.o.x, r.o.y, r.o.z, r.d.x, r.d.y, r.d.z);
     if (!(h.y < RTB_INF)) return false;
@@ -689,8 +724,8 @@ RTB_DEV_NOINLINE MediaEvent sample_media_general(const DSceneView& S, float ox, 
 // persistent kernel's shade phase costs it 240 B of stack frame and 150 B of spills), MEDIA_GENERAL = it knows it is,
 // MEDIA_ANY = decide here from the scene's flag.
 enum { MEDIA_FAST = 0, MEDIA_GENERAL = 1, MEDIA_ANY = 2 };
-template <int MODE = MEDIA_ANY>
-RTB_DEV void sample_media(const DSceneView& S, const Ray& r, float tmin, const PathRng& rng, float& t_best, int& medium_best) {
+template <int MODE = MEDIA_ANY, class SV = DSceneView>
+RTB_DEV void sample_media(const SV& S, const Ray& r, float tmin, const PathRng& rng, float& t_best, int& medium_best) {
     if (MODE == MEDIA_GENERAL || (MODE == MEDIA_ANY && S.media_general)) {
         const MediaEvent ev = sample_media_general(S, r.o.x, r.o.y, r.o.z, r.d.x, r.d.y, r.d.z, tmin, rng.pixel, rng.sample, rng.draw, rng.k0, rng.k1, t_best);
         t_best = ev.t, medium_best = ev.medium;
@@ -786,9 +821,10 @@ RTB_DEV float noise_value(const DTexture& T, V3 p, float turbulence) {  // Noise
 }
 
 // req == nullptr: evaluate everything here.  Otherwise a NOISE leaf is left pending in *req and white is returned.
-RTB_DEV V3 texture_leaf(const DSceneView& S, int tex, float u, float v, V3 p, NoiseReq* req) {
+template <class SV>
+RTB_DEV V3 texture_leaf(const SV& S, int tex, float u, float v, V3 p, NoiseReq* req) {
     const DTexture& T = S.texs[tex];
-    if (T.kind == TEX_NOISE) {
+    if ((SV::feat & F_NOISE) && T.kind == TEX_NOISE) {
         if (req) {
             req->tex = tex, req->p = p;
             return v3(1.f, 1.f, 1.f);
@@ -798,7 +834,7 @@ RTB_DEV V3 texture_leaf(const DSceneView& S, int tex, float u, float v, V3 p, No
         float g = noise_value(T, p, perlin_turbulence(vec, perm, T.scale * p));
         return v3(g, g, g);
     }
-    if (T.kind == TEX_IMAGE) {  // image_texture.rs:16-28 — nearest texel, v flipped
+    if ((SV::feat & F_IMAGE) && T.kind == TEX_IMAGE) {  // image_texture.rs:16-28 — nearest texel, v flipped
         const DImage& im = S.images[T.a];
         u = fminf(fmaxf(u, 0.0f), 1.0f);
         v = fminf(fmaxf(1.0f - v, 0.0f), 1.0f);
@@ -812,15 +848,17 @@ RTB_DEV V3 texture_leaf(const DSceneView& S, int tex, float u, float v, V3 p, No
     return v3(T.color[0], T.color[1], T.color[2]);
 }
 
-RTB_DEV V3 texture_value(const DSceneView& S, int tex, float u, float v, V3 p, NoiseReq* req = nullptr) {
-    if (S.texs[tex].kind == TEX_CHECKER) {  // textures.rs:40-49; nested checkers see the same p, hence the same side
+template <class SV>
+RTB_DEV V3 texture_value(const SV& S, int tex, float u, float v, V3 p, NoiseReq* req = nullptr) {
+    if ((SV::feat & F_CHECKER) && S.texs[tex].kind == TEX_CHECKER) {  // textures.rs:40-49; nested checkers see the same p, hence the same side
         const float sines = sin_accurate(5.0f * p.x) * sin_accurate(5.0f * p.y) * sin_accurate(5.0f * p.z);
         for (int level = 0; level < RTB_CHECKER_DEPTH && S.texs[tex].kind == TEX_CHECKER; ++level) tex = sines < 0.0f ? S.texs[tex].a : S.texs[tex].b;
     }
     return texture_leaf(S, tex, u, v, p, req);
 }
 
-RTB_DEV bool texture_needs_uv(const DSceneView& S, int tex) { return S.texs[tex].needs_uv != 0; }
+template <class SV>
+RTB_DEV bool texture_needs_uv(const SV& S, int tex) { return (SV::feat & F_IMAGE) && S.texs[tex].needs_uv != 0; }
 
 // ------------------------------------------------------------------ hit attributes (hittable.rs:18-30 + transforms)
 struct Surface {
@@ -829,13 +867,14 @@ struct Surface {
     bool front;
 };
 
-RTB_DEV void surface_at(const DSceneView& S, const PrimRec& P, const Ray& r, float t, int face, bool want_uv, Surface& s) {
-    int inst = prim_instance(P);
+template <class SV>
+RTB_DEV void surface_at(const SV& S, const PrimRec& P, const Ray& r, float t, int face, bool want_uv, Surface& s) {
+    const int inst = (SV::feat & F_INSTANCE) ? prim_instance(P) : 0;
     V3 ng;         // geometric normal in world space (the reference's "outward" one)
     V3 n_obj_out;  // outward normal in object space (for sphere uv)
     s.p = r.o + t * r.d;
     s.u = 0.0f, s.v = 0.0f;
-    if ((P.meta & PRIM_KIND_MASK) == PRIM_SPHERE) {
+    if (!(SV::feat & F_BOX) || ((SV::feat & F_SPHERE) && (P.meta & PRIM_KIND_MASK) == PRIM_SPHERE)) {
         float inv_r = 1.0f / P.v3;  // signed radius flips the normal (shapes.rs:78)
         ng = (s.p - v3(P.v0, P.v1, P.v2)) * inv_r;
         n_obj_out = inst ? mul33t(S.inst[inst - 1].rot, ng) : ng;
@@ -852,7 +891,7 @@ RTB_DEV void surface_at(const DSceneView& S, const PrimRec& P, const Ray& r, flo
             else if (k == 1) s.p.y = plane;
             else s.p.z = plane;
         }
-        if (want_uv) {
+        if ((SV::feat & F_UVBOX) && want_uv) {
             Ray ro = to_object_space(S, inst, r);
             V3 po = ro.o + t * ro.d;
             int a0 = k == 0 ? 1 : 0, a1 = k == 2 ? 1 : 2;
@@ -885,14 +924,16 @@ struct PathState {
     float time;       // EXTENSION: the path's time in [0, 1] (moving spheres); 0 without a shutter
 };
 
-RTB_DEV V3 background_color(const DSceneView& S, const Ray& r) {  // raytrace.rs:29-35, :44-48
+template <class SV>
+RTB_DEV V3 background_color(const SV& S, const Ray& r) {  // raytrace.rs:29-35, :44-48
     if (S.bg_kind == 0) return v3(0.f, 0.f, 0.f);
     float t = 0.5f * (normalize(r.d).y + 1.0f);
     return v3((1.0f - t) * S.bg_bottom[0] + t * S.bg_top[0], (1.0f - t) * S.bg_bottom[1] + t * S.bg_top[1],
               (1.0f - t) * S.bg_bottom[2] + t * S.bg_top[2]);
 }
 
-RTB_DEV V3 material_color(const DSceneView& S, const DMaterial& M, const Surface& s, NoiseReq* req = nullptr) {
+template <class SV>
+RTB_DEV V3 material_color(const SV& S, const DMaterial& M, const Surface& s, NoiseReq* req = nullptr) {
     if (M.tex < 0) return v3(M.albedo[0], M.albedo[1], M.albedo[2]);
     return texture_value(S, M.tex, s.u, s.v, s.p, req);
 }
@@ -900,7 +941,8 @@ RTB_DEV V3 material_color(const DSceneView& S, const DMaterial& M, const Surface
 // Material::scatter / emit at a surface or medium event.  Returns true when the path goes on (ps updated);
 // otherwise `radiance` is the terminal term (emission, or 0 for an absorbed metal reflection).
 // With `req`, a noise texture is left pending: the caller multiplies ps.beta (alive) or radiance (emitter) by it.
-RTB_DEV bool scatter(const DSceneView& S, const DMaterial& M, const Surface& s, const float u[4], PathState& ps, int prim, int face, V3& radiance,
+template <class SV>
+RTB_DEV bool scatter(const SV& S, const DMaterial& M, const Surface& s, const float u[4], PathState& ps, int prim, int face, V3& radiance,
                      NoiseReq* req = nullptr) {
     // Branch-light: what several material kinds need is computed once by every lane (the lanes of a warp shade
     // different materials side by side), the kinds then differ by a few selects.
@@ -950,10 +992,11 @@ RTB_DEV bool scatter(const DSceneView& S, const DMaterial& M, const Surface& s, 
 
 // Material::scatter / emit for the event the extend stage found: a medium event (volumes.rs:55-63: normal (1,0,0),
 // front_face, u = v = 0) or a surface hit.  ONE scatter call site for both.
-RTB_DEV bool scatter_event(const DSceneView& S, int medium, int prim, int face, float t, const float u[4], PathState& ps, V3& radiance, NoiseReq* req) {
+template <class SV>
+RTB_DEV bool scatter_event(const SV& S, int medium, int prim, int face, float t, const float u[4], PathState& ps, V3& radiance, NoiseReq* req) {
     Surface sf;
     int mat_index;
-    if (medium >= 0) {
+    if ((SV::feat & F_MEDIA) && medium >= 0) {
         mat_index = (int)as_uint(ld4(reinterpret_cast<const char*>(S.media + medium) + 32).y);
         sf.p = ps.ray.o + t * ps.ray.d;
         sf.n = v3(1.f, 0.f, 0.f), sf.u = 0.f, sf.v = 0.f, sf.front = true;
@@ -971,7 +1014,8 @@ RTB_DEV bool scatter_event(const DSceneView& S, int medium, int prim, int face, 
 
 // One path segment: nearest surface, media, then scatter.  Returns true while the path is alive; when it
 // ends, `radiance` holds beta * terminal term.
-RTB_DEV bool extend_and_shade(const DSceneView& S, PathState& ps, PathRng& rng, int segment, V3& radiance) {
+template <class SV>
+RTB_DEV bool extend_and_shade(const SV& S, PathState& ps, PathRng& rng, int segment, V3& radiance) {
     if (ps.depth <= 0) {  // depth exhausted: Color::ZERO (raytrace.rs:87-89)
         radiance = v3(0.f, 0.f, 0.f);
         return false;
@@ -984,7 +1028,7 @@ RTB_DEV bool extend_and_shade(const DSceneView& S, PathState& ps, PathRng& rng, 
     float t = RTB_INF;
     int medium = -1;
     rng.draw = 1u + 2u * (uint32_t)segment;
-    if (S.n_media > 0) {
+    if ((SV::feat & F_MEDIA) && S.n_media > 0) {
         sample_media(S, ps.ray, RTB_T_MIN, rng, t, medium);
     }
     int prim, face;
@@ -1031,7 +1075,8 @@ RTB_DEV bool item_to_pixel(const DRenderParams& P, long long item, int& px, int&
 // render_pixel's sample loop (raytrace.rs:188-198) for samples [first, first + count) of one pixel.
 // Paths are regenerated in place: every loop iteration advances whatever path the thread currently holds by
 // one segment, so the lanes of a warp stay busy until their whole run of samples is finished.
-RTB_DEV void integrate_item(const DSceneView& S, const DCamera& cam, const DRenderParams& P, int px, int py, int first, int count, AccumFx sum[3],
+template <class SV>
+RTB_DEV void integrate_item(const SV& S, const DCamera& cam, const DRenderParams& P, int px, int py, int first, int count, AccumFx sum[3],
                             uint32_t& n_rays) {
     PathRng rng;
     rng.pixel = (uint32_t)(py * P.width + px);
@@ -1089,11 +1134,11 @@ RTB_DEV float4 f4(float x, float y, float z, float w) {
 
 // the closest medium event along the slot's (new) ray, drawn with the media uniforms of segment `segment`; it
 // becomes the t_max (and fallback hit code) of the surface search in the extend stage
-template <int MODE = MEDIA_ANY>
-RTB_DEV void wf_presample_media(const DSceneView& S, const DRenderParams& P, WfSlot& s, int segment) {
+template <int MODE = MEDIA_ANY, class SV = DSceneView>
+RTB_DEV void wf_presample_media(const SV& S, const DRenderParams& P, WfSlot& s, int segment) {
     float t = RTB_INF;
     int medium = -1;
-    if (S.n_media > 0) {
+    if ((SV::feat & F_MEDIA) && S.n_media > 0) {
         Ray r;
         r.o = v3(s.A.x, s.A.y, s.A.z), r.d = v3(s.B.x, s.B.y, s.B.z);
         PathRng rng;
@@ -1105,20 +1150,23 @@ RTB_DEV void wf_presample_media(const DSceneView& S, const DRenderParams& P, WfS
 }
 
 // a fresh camera path for (pixel, sample)
-RTB_DEV void wf_init_pixel_sample(const DSceneView& S, const DCamera& cam, const DRenderParams& P, uint32_t pixel, uint32_t sample, WfSlot& s);
+template <class SV>
+RTB_DEV void wf_init_pixel_sample(const SV& S, const DCamera& cam, const DRenderParams& P, uint32_t pixel, uint32_t sample, WfSlot& s);
 
 // a fresh camera path: global path number -> (pixel, sample); sample-major so that consecutive paths are
 // neighbouring pixels of one sample index
-RTB_DEV void wf_init_path(const DSceneView& S, const DCamera& cam, const DRenderParams& P, unsigned long long path, WfSlot& s) {
+template <class SV>
+RTB_DEV void wf_init_path(const SV& S, const DCamera& cam, const DRenderParams& P, unsigned long long path, WfSlot& s) {
     unsigned long long npix = (unsigned long long)P.width * (unsigned long long)P.height;
     wf_init_pixel_sample(S, cam, P, (uint32_t)(path % npix), (uint32_t)P.sample_begin + (uint32_t)(path / npix), s);
 }
 
 // the camera ray alone (the caller pre-samples the media of segment 0)
+template <uint32_t FEAT = F_ALL>
 RTB_DEV void wf_init_camera(const DCamera& cam, const DRenderParams& P, uint32_t pixel, uint32_t sample, WfSlot& s) {
     PathRng rng;
     rng.pixel = pixel, rng.sample = sample, rng.draw = 0, rng.k0 = P.seed_lo, rng.k1 = P.seed_hi;
-    const uint32_t time_bits = camera_time_flags(cam, rng);
+    const uint32_t time_bits = (FEAT & F_MOVING) ? camera_time_flags(cam, rng) : 0u;  // nothing moves: nothing reads the path's time
     float u[4];
     rng_next4(rng, u);
     Ray r = generate_camera_ray(cam, P, (int)(pixel % (uint32_t)P.width), (int)(pixel / (uint32_t)P.width), u);
@@ -1128,7 +1176,8 @@ RTB_DEV void wf_init_camera(const DCamera& cam, const DRenderParams& P, uint32_t
     s.D = f4(0.f, 0.f, as_float(0xFFFFFFFFu), 0.f);
 }
 
-RTB_DEV void wf_init_pixel_sample(const DSceneView& S, const DCamera& cam, const DRenderParams& P, uint32_t pixel, uint32_t sample, WfSlot& s) {
+template <class SV>
+RTB_DEV void wf_init_pixel_sample(const SV& S, const DCamera& cam, const DRenderParams& P, uint32_t pixel, uint32_t sample, WfSlot& s) {
     wf_init_camera(cam, P, pixel, sample, s);
     wf_presample_media(S, P, s, 0);
 }
@@ -1136,7 +1185,8 @@ RTB_DEV void wf_init_pixel_sample(const DSceneView& S, const DCamera& cam, const
 // end of the extend stage for one ray: final hit code and the queue class the shade stage picks the path up from.
 // prim/face/mat describe the closest surface found below the incoming t_max (prim < 0: none, the incoming code
 // — a medium event or a miss — stands).
-RTB_DEV int wf_classify(const DSceneView& S, int prim, int face, int mat, int code_in, int& code_out) {
+template <class SV>
+RTB_DEV int wf_classify(const SV& S, int prim, int face, int mat, int code_in, int& code_out) {
     if (prim >= 0) {
         code_out = prim | (face << 24);
     } else {
@@ -1152,7 +1202,8 @@ RTB_DEV int wf_classify(const DSceneView& S, int prim, int face, int mat, int co
 // the shade stage for one path: scatter or terminate.  Returns true while alive (slot updated in place, media
 // event of the new ray pre-sampled); otherwise `radiance` is the path's contribution to its pixel.
 // wf_shade_core: everything but the media pre-sampling of the new ray; `segment_next` = its segment number.
-RTB_DEV bool wf_shade_core(const DSceneView& S, const DRenderParams& P, WfSlot& s, V3& radiance, NoiseReq* req, int& segment_next) {
+template <class SV>
+RTB_DEV bool wf_shade_core(const SV& S, const DRenderParams& P, WfSlot& s, V3& radiance, NoiseReq* req, int& segment_next) {
     PathState ps;
     ps.ray.o = v3(s.A.x, s.A.y, s.A.z), ps.ray.d = v3(s.B.x, s.B.y, s.B.z);
     ps.beta = v3(s.C.x, s.C.y, s.C.z);
@@ -1192,18 +1243,59 @@ RTB_DEV bool wf_shade_core(const DSceneView& S, const DRenderParams& P, WfSlot& 
     return true;
 }
 
-RTB_DEV bool wf_shade(const DSceneView& S, const DRenderParams& P, WfSlot& s, V3& radiance) {
+template <class SV>
+RTB_DEV bool wf_shade(const SV& S, const DRenderParams& P, WfSlot& s, V3& radiance) {
     int segment_next;
     if (!wf_shade_core(S, P, s, radiance, nullptr, segment_next)) return false;
     wf_presample_media(S, P, s, segment_next);
     return true;
 }
 
+// Event-to-event advance inside a CLEAR medium (DSceneView.clear_media, flatten.cpp: find_clear_media).  The slot holds a
+// path whose ray starts inside medium m's boundary and whose pre-sampled event (D.x, D.y = WF_MEDIUM | m) lies inside it
+// as well: the boundary is one convex primitive with nothing else inside, so the surface search of the extend stage
+// cannot find anything closer and is skipped.  One step = exactly what wf_shade does for such a slot (isotropic scatter,
+// volumes.rs:77-83, then the media pre-sampling of the new ray) with the same Philox counters, minus everything a
+// medium event never needs (surface attributes, textures, the other material kinds).
+// Returns 0: the path ended (depth exhausted, contributes Color::ZERO), 1: the new ray's event is again inside medium m
+// (the slot is ready for another step), 2: it is not (the slot is an ordinary ready path for the extend stage).
+template <class SV>
+RTB_DEV bool wf_chain_eligible(const SV& S, int code_shaded, const WfSlot& s_next) {
+    return code_shaded >= 0 && (code_shaded & WF_MEDIUM) != 0 && (code_shaded & 0xFFFF) < 32 && ((S.clear_media >> (code_shaded & 31)) & 1u) != 0u &&
+           (int)as_uint(s_next.D.y) == code_shaded;
+}
+template <int MODE = MEDIA_ANY, class SV = DSceneView>
+RTB_DEV int wf_chain_step(const SV& S, const DRenderParams& P, WfSlot& s) {
+    const uint32_t flags = as_uint(s.B.w);
+    int depth = (int)(flags & WF_DEPTH_MASK);
+    const int segment = P.max_depth - depth;
+    depth -= 1;
+    const int code = (int)as_uint(s.D.y);
+    PathRng rng;
+    rng.pixel = as_uint(s.A.w), rng.sample = as_uint(s.C.w), rng.draw = 2u + 2u * (uint32_t)segment, rng.k0 = P.seed_lo, rng.k1 = P.seed_hi;
+    float us[4];
+    rng_next4(rng, us);
+    const int mat_index = (int)as_uint(ld4(reinterpret_cast<const char*>(S.media + (code & 0xFFFF)) + 32).y);
+    const float4 albedo = ld4(reinterpret_cast<const char*>(S.mats + mat_index) + 16);  // albedo.rgb, pad
+    const float t = s.D.x;
+    const V3 p = v3(s.A.x, s.A.y, s.A.z) + t * v3(s.B.x, s.B.y, s.B.z);
+    const V3 dir = sample_unit_ball(us[0], us[1], us[2]);
+    const V3 beta = v3(s.C.x, s.C.y, s.C.z) * v3(albedo.x, albedo.y, albedo.z);
+    if (depth <= 0) return 0;
+    s.A = f4(p.x, p.y, p.z, s.A.w);
+    s.B = f4(dir.x, dir.y, dir.z, as_float((uint32_t)depth | (flags & WF_TIME_MASK)));
+    s.C = f4(beta.x, beta.y, beta.z, s.C.w);
+    s.D.z = as_float(0xFFFFFFFFu);
+    wf_presample_media<MODE>(S, P, s, segment + 1);
+    return (int)as_uint(s.D.y) == code ? 1 : 2;
+}
+
 // ------------------------------------------------------------------ test entry points (rt_intersect_batch etc.)
 enum { QUERY_BVH = 0, QUERY_LINEAR = 1, QUERY_MEDIUM = 2, QUERY_BVH4 = 3 };
 
 // Hittable::hit for one ray given as 8 floats (origin, direction, t_min, t_max) -> RtHit
-RTB_DEV void intersect_query(const DSceneView& S, int mode, const float* q, RtHit& out, float time = 0.0f) {
+template <class SV>
+RTB_DEV void intersect_query(const SV& S, int mode, const float* q, RtHit& out, float time = 0.0f) {
     Ray r;
     r.o = v3(q[0], q[1], q[2]), r.d = v3(q[3], q[4], q[5]);
     float tmin = q[6], tmax = q[7];
@@ -1231,7 +1323,8 @@ RTB_DEV void intersect_query(const DSceneView& S, int mode, const float* q, RtHi
 }
 
 // Material::scatter / emit for one caller-supplied hit (rt_scatter_batch): the very `scatter` the pipelines call
-RTB_DEV void scatter_query(const DSceneView& S, const RtScatterIn& in, RtScatterOut& out) {
+template <class SV>
+RTB_DEV void scatter_query(const SV& S, const RtScatterIn& in, RtScatterOut& out) {
     Surface sf;
     sf.p = v3(in.p[0], in.p[1], in.p[2]), sf.n = v3(in.normal[0], in.normal[1], in.normal[2]);
     sf.u = in.u, sf.v = in.v, sf.front = in.front_face != 0;

@@ -17,6 +17,7 @@
 #include <cuda_runtime.h>
 
 #include <algorithm>
+#include <map>
 #include <cstdio>
 #include <cstdlib>
 
@@ -35,11 +36,18 @@ namespace rtb {
 #define PS_MIN_BLOCKS 6
 #define PS_CHUNK 256u      // camera paths a warp reserves per atomic
 
-enum { ST_EMPTY = 0, ST_TRAV = 1, ST_DONE = 2, ST_READY = 3 };
+// chain phase (paths that hop from event to event inside a clear medium, rt_device.cuh: wf_chain_step)
+#define PS_CHAIN_TRIG 24   // parked chain paths in the warp that start a chain phase ...
+#define PS_CHAIN_MIN 12    // ... which goes on while at least this many lanes still hold one
 
-// scheduling thresholds (defaults = the PS_* constants; RT_PS_WORK / RT_PS_STALL / RT_PS_LEAVE / RT_PS_DESCEND override them for sweeps)
+// ST_CHAIN: a finished "traversal" whose hit is the pre-sampled event of a clear medium the ray starts inside — the record
+// is what ST_DONE holds, but the chain phase advances it without the shade phase and without a surface search
+enum { ST_EMPTY = 0, ST_TRAV = 1, ST_DONE = 2, ST_READY = 3, ST_CHAIN = 4 };
+
+// scheduling thresholds (defaults = the PS_* constants; RT_PS_WORK / RT_PS_STALL / RT_PS_LEAVE / RT_PS_DESCEND / RT_PS_CHAIN_TRIG /
+// RT_PS_CHAIN_MIN override them for sweeps; RT_PS_CHAIN_TRIG=0 turns the chain phase off)
 struct PsTune {
-    int work, stall, leave, descend;
+    int work, stall, leave, descend, chain_trig, chain_min;
 };
 
 struct PsCounters {
@@ -52,25 +60,26 @@ struct PsCounters {
 #define PS_MAX_SMEM (227u * 1024u)
 struct PersistState {
     PsCounters* ctr = nullptr;
-    int blocks[PS_VARIANTS] = {};  // resident grid of each kernel instance (0 = not queried yet)
+    std::map<const void*, int> blocks;  // resident grid of each kernel instance launched so far
 };
 
 // One camera path = one record of PS_REC words in shared memory, SoA over the block's threads (conflict-free):
 //   origin.xyz, direction.xyz, beta.rgb, t, pixel, sample, flags (depth left | origin face << 16), origin primitive, hit
-// hit: -1 miss, prim | face << 24 surface, WF_MEDIUM | m medium (as in WfSlot.D.y).  Every lane owns PS_SLOTS records;
-// the slot statuses live in one register (2 bits per slot).  Registers hold only the context of the traversal in
+// hit: -1 miss, prim | face << 24 surface, WF_MEDIUM | m medium (as in WfSlot.D.y).  Every lane owns NS records (2 or 3);
+// the slot statuses live in one register (4 bits per slot).  Registers hold only the context of the traversal in
 // flight (ray, node-test constants, closest hit so far, cursor), so shading a parked path moves nothing around.
 enum { R_OX, R_OY, R_OZ, R_DX, R_DY, R_DZ, R_BR, R_BG, R_BB, R_T, R_PIXEL, R_SAMPLE, R_FLAGS, R_ORIGIN, R_HIT, PS_REC };
-#define PS_SLOTS 2
-// field `f` of record `slot` of the calling thread; the pool is [PS_SLOTS][PS_REC][NT] floats at the start of shared memory
+#define PS_MAX_SLOTS 4
+// field `f` of record `slot` of the calling thread; the pool is [NS][PS_REC][NT] floats at the start of shared memory
 #define POOL(slot, f) pool[((slot) * PS_REC + (f)) * NT + threadIdx.x]
 
-__device__ __forceinline__ int slot_status(unsigned int stat, int s) { return (int)((stat >> (2 * s)) & 3u); }
-__device__ __forceinline__ unsigned int slot_set(unsigned int stat, int s, int st) { return (stat & ~(3u << (2 * s))) | ((unsigned int)st << (2 * s)); }
+__device__ __forceinline__ int slot_status(unsigned int stat, int s) { return (int)((stat >> (4 * s)) & 15u); }
+__device__ __forceinline__ unsigned int slot_set(unsigned int stat, int s, int st) { return (stat & ~(15u << (4 * s))) | ((unsigned int)st << (4 * s)); }
+template <int NS>
 __device__ __forceinline__ int slot_find(unsigned int stat, int want) {  // lowest slot with that status, -1 if none
     int found = -1;
 #pragma unroll
-    for (int s = PS_SLOTS - 1; s >= 0; --s)
+    for (int s = NS - 1; s >= 0; --s)
         if (slot_status(stat, s) == want) found = s;
     return found;
 }
@@ -90,6 +99,24 @@ __device__ __forceinline__ void rec_store(float* pool, int slot, const WfSlot& s
     POOL(slot, R_T) = s.D.x, POOL(slot, R_HIT) = s.D.y, POOL(slot, R_ORIGIN) = s.D.z;
 }
 
+// the same for a record in another lane's column `col` (index of its owner within the block): the chain phase hands the
+// parked chain records of the warp to its lowest lanes
+#define POOLC(slot, f, col) pool[((slot) * PS_REC + (f)) * NT + (col)]
+template <int NT>
+__device__ __forceinline__ void rec_load_col(const float* pool, int slot, int col, WfSlot& s) {
+    s.A = f4(POOLC(slot, R_OX, col), POOLC(slot, R_OY, col), POOLC(slot, R_OZ, col), POOLC(slot, R_PIXEL, col));
+    s.B = f4(POOLC(slot, R_DX, col), POOLC(slot, R_DY, col), POOLC(slot, R_DZ, col), POOLC(slot, R_FLAGS, col));
+    s.C = f4(POOLC(slot, R_BR, col), POOLC(slot, R_BG, col), POOLC(slot, R_BB, col), POOLC(slot, R_SAMPLE, col));
+    s.D = f4(POOLC(slot, R_T, col), POOLC(slot, R_HIT, col), POOLC(slot, R_ORIGIN, col), 0.f);
+}
+template <int NT>
+__device__ __forceinline__ void rec_store_col(float* pool, int slot, int col, const WfSlot& s) {
+    POOLC(slot, R_OX, col) = s.A.x, POOLC(slot, R_OY, col) = s.A.y, POOLC(slot, R_OZ, col) = s.A.z;
+    POOLC(slot, R_DX, col) = s.B.x, POOLC(slot, R_DY, col) = s.B.y, POOLC(slot, R_DZ, col) = s.B.z, POOLC(slot, R_FLAGS, col) = s.B.w;
+    POOLC(slot, R_BR, col) = s.C.x, POOLC(slot, R_BG, col) = s.C.y, POOLC(slot, R_BB, col) = s.C.z;
+    POOLC(slot, R_T, col) = s.D.x, POOLC(slot, R_HIT, col) = s.D.y, POOLC(slot, R_ORIGIN, col) = s.D.z;
+}
+
 // 128-bit load from a shared-memory address (the scene copy of the SCENE variants)
 __device__ __forceinline__ float4 lds4(uint32_t saddr) {
     float4 v;
@@ -102,23 +129,21 @@ __device__ __forceinline__ float4 lds4(uint32_t saddr) {
 __device__ __forceinline__ float warp_turbulence(const float* __restrict__ vec, const unsigned short* __restrict__ perm, V3 p) {
     const int lane = (int)(threadIdx.x & 31u);
     float acc = 0.0f;
-#pragma unroll
-    for (int base = 0; base < 56; base += 32) {
-        const int term = base + lane;
-        if (term < 56) {
-            const int oct = term >> 3, di = (term >> 2) & 1, dj = (term >> 1) & 1, dk = term & 1;
-            const float scale = (float)(1 << oct);
-            const float qx = p.x * scale, qy = p.y * scale, qz = p.z * scale;  // exact: the reference doubles p per octave
-            const float fx = floorf(qx), fy = floorf(qy), fz = floorf(qz);
-            const float u = qx - fx, v = qy - fy, w = qz - fz;
-            const int i = (int)fx, j = (int)fy, k = (int)fz;
-            const float uu = u * u * (3.0f - 2.0f * u), vv = v * v * (3.0f - 2.0f * v), ww = w * w * (3.0f - 2.0f * w);
-            const int idx = perm[(i + di) & 1023] ^ perm[1024 + ((j + dj) & 1023)] ^ perm[2048 + ((k + dk) & 1023)];
-            const float4 g = ld4(vec + 4 * idx);
-            const float wx = u - (float)di, wy = v - (float)dj, wz = w - (float)dk;
-            const float bi = di ? uu : 1.0f - uu, bj = dj ? vv : 1.0f - vv, bk = dk ? ww : 1.0f - ww;
-            acc += (1.0f / scale) * (bi * bj * bk * (wx * g.x + wy * g.y + wz * g.z));
-        }
+    // two rounds of 32 terms, NOT unrolled: the kernel's speed hangs on its instruction footprint (32 KB instruction cache)
+#pragma unroll 1
+    for (int term = lane; term < 56; term += 32) {
+        const int oct = term >> 3, di = (term >> 2) & 1, dj = (term >> 1) & 1, dk = term & 1;
+        const float scale = (float)(1 << oct);
+        const float qx = p.x * scale, qy = p.y * scale, qz = p.z * scale;  // exact: the reference doubles p per octave
+        const float fx = floorf(qx), fy = floorf(qy), fz = floorf(qz);
+        const float u = qx - fx, v = qy - fy, w = qz - fz;
+        const int i = (int)fx, j = (int)fy, k = (int)fz;
+        const float uu = u * u * (3.0f - 2.0f * u), vv = v * v * (3.0f - 2.0f * v), ww = w * w * (3.0f - 2.0f * w);
+        const int idx = perm[(i + di) & 1023] ^ perm[1024 + ((j + dj) & 1023)] ^ perm[2048 + ((k + dk) & 1023)];
+        const float4 g = ld4(vec + 4 * idx);
+        const float wx = u - (float)di, wy = v - (float)dj, wz = w - (float)dk;
+        const float bi = di ? uu : 1.0f - uu, bj = dj ? vv : 1.0f - vv, bk = dk ? ww : 1.0f - ww;
+        acc += (1.0f / scale) * (bi * bj * bk * (wx * g.x + wy * g.y + wz * g.z));
     }
 #pragma unroll
     for (int off = 16; off > 0; off >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, off);
@@ -129,19 +154,71 @@ __global__ void ps_reset_kernel(PsCounters* c, unsigned long long total) { c->ne
 
 // phase statistics of a debug launch (RT_PS_STATS=1): warp-level step counts and the lanes that were useful in them
 enum { PSS_SHADE_PHASES, PSS_SHADE_ACT, PSS_SHADE_DONE, PSS_SHADE_ONPARK, PSS_EXT_PHASES, PSS_INNER_ITERS, PSS_INNER_LANES, PSS_LEAF_STEPS,
-       PSS_LEAF_LANES, PSS_LEAF_PRIMS, PSS_EXT_ROUNDS, PSS_EXT_TRAV_LANES, PSS_NOISE, PSS_COUNT };
+       PSS_LEAF_LANES, PSS_LEAF_PRIMS, PSS_EXT_ROUNDS, PSS_EXT_TRAV_LANES, PSS_NOISE, PSS_CHAIN_PHASES, PSS_CHAIN_RECORDS, PSS_CHAIN_ITERS, PSS_CHAIN_LANES,
+       PSS_CHAIN_PARKED, PSS_COUNT };
+
+// ---------------------------------------------------------------------------------------------------------------
+// Chain phase.  The parked chain records of the warp (ST_CHAIN, wherever they live) go to its lowest lanes, which advance
+// them event by event (wf_chain_step: two Philox blocks, one in-ball direction, the media intervals — ~200 instructions
+// a step instead of a traversal and a share of a shade phase) while at least `min_lanes` are left.
+template <int NT, int NS, int MEDIA, bool STATS, class SV>
+__device__ __forceinline__ uint2 chain_phase(float* pool, const SV& S, const DRenderParams& P, int min_lanes, unsigned int stat, unsigned int* st_) {
+    const unsigned int lane = threadIdx.x & 31u;
+    // lane i takes the i-th parked record, slot 0's first
+    int src_slot = -1, src_lane = 0, before = 0, n_chain = 0;
+#pragma unroll
+    for (int k = 0; k < NS; ++k) {
+        const unsigned int mk = __ballot_sync(0xffffffffu, slot_status(stat, k) == ST_CHAIN);
+        const int nk = __popc(mk);
+        if (src_slot < 0 && (int)lane < before + nk) src_slot = k, src_lane = (int)__fns(mk, 0u, (int)lane - before + 1);
+        before += nk;
+    }
+    n_chain = before;
+    const bool mine = src_slot >= 0;
+    if (!mine) src_slot = 0;
+    const int col = (int)(threadIdx.x & ~31u) + src_lane;
+    if (STATS && lane == 0) st_[PSS_CHAIN_PHASES] += 1u, st_[PSS_CHAIN_RECORDS] += (unsigned int)(n_chain < 32 ? n_chain : 32), st_[PSS_CHAIN_PARKED] += (unsigned int)n_chain;
+    __syncwarp();
+    WfSlot s;
+    s.A = s.B = s.C = s.D = f4(0.f, 0.f, 0.f, 0.f);
+    if (mine) rec_load_col<NT>(pool, src_slot, col, s);
+    int state = mine ? 1 : -1;  // 1: still hopping, 2: left the medium (ready for the extend stage), 0: ended
+    unsigned int rays = 0u;
+    for (;;) {
+        const unsigned int m_act = __ballot_sync(0xffffffffu, state == 1);
+        if (__popc(m_act) < min_lanes) break;
+        if (STATS && lane == 0) st_[PSS_CHAIN_ITERS] += 1u, st_[PSS_CHAIN_LANES] += (unsigned int)__popc(m_act);
+        if (state == 1) {
+            rays += 1u;
+            const int rc = wf_chain_step<MEDIA>(S, P, s);
+            state = rc == 1 ? 1 : (rc == 2 ? 2 : 0);
+        }
+    }
+    if (mine && state != 0) rec_store_col<NT>(pool, src_slot, col, s);
+    const unsigned int bit = 1u << src_lane;
+#pragma unroll
+    for (int k = 0; k < NS; ++k) {
+        const unsigned int ready = __reduce_or_sync(0xffffffffu, (mine && state == 2 && src_slot == k) ? bit : 0u);
+        const unsigned int ended = __reduce_or_sync(0xffffffffu, (mine && state == 0 && src_slot == k) ? bit : 0u);
+        if ((ready >> lane) & 1u) stat = slot_set(stat, k, ST_READY);
+        if ((ended >> lane) & 1u) stat = slot_set(stat, k, ST_EMPTY);
+    }
+    __syncwarp();
+    return make_uint2(stat, rays);
+}
 
 // WIDE: walk the 4-wide tree (DNode4) with 4-byte stack keys, the first SD stack levels in shared memory (the rest, if a
 // ray ever needs them, in local memory); !WIDE: the binary 32-byte-node tree with (link, distance) entries in local memory.
 // NT threads per block.  SCENE bit 0: the block keeps a copy of the DNode4 array in shared memory, bit 1: of the
 // primitives — ONE large block per SM then shares a single copy, and the L1 that is left holds only what is not copied.
-// Dynamic shared memory: [pool PS_SLOTS x PS_REC x NT floats][stack SD x NT keys][nodes4][prims].
+// Dynamic shared memory: [pool NS x PS_REC x NT floats][stack SD x NT keys][nodes4][prims].
 #define PS_SCENE_NODES 1
 #define PS_SCENE_PRIMS 2
-template <bool STATS, bool WIDE, int SD, int NT, int SCENE, int MEDIA>
-__global__ void __launch_bounds__(NT, (STATS || NT > 128) ? 1 : PS_MIN_BLOCKS) persist_kernel(DSceneView S, DCamera cam, DRenderParams P, PsCounters* __restrict__ ctr,
+template <bool STATS, bool WIDE, int SD, int NT, int SCENE, int MEDIA, int NS, bool CHAIN, uint32_t FEAT>
+__global__ void __launch_bounds__(NT, (STATS || NT > 128) ? 1 : PS_MIN_BLOCKS) persist_kernel(DSceneView S_, DCamera cam, DRenderParams P, PsCounters* __restrict__ ctr,
                                                              AccumFx* __restrict__ accum, unsigned long long* __restrict__ rays_out,
                                                              unsigned int chunk_size, unsigned long long* __restrict__ stats, PsTune tune) {
+    const SceneViewF<FEAT>& S = static_cast<const SceneViewF<FEAT>&>(S_);  // same record; SV::feat = what the scene can contain (rt_types.h)
     unsigned int st_[PSS_COUNT];
     if (STATS)
         for (int k = 0; k < PSS_COUNT; ++k) st_[k] = 0u;
@@ -152,7 +229,7 @@ __global__ void __launch_bounds__(NT, (STATS || NT > 128) ? 1 : PS_MIN_BLOCKS) p
     }
     extern __shared__ float4 smem_raw[];
     float* const pool = reinterpret_cast<float*>(smem_raw);
-    uint32_t* const sstack = reinterpret_cast<uint32_t*>(pool + PS_SLOTS * PS_REC * NT);  // [SD][NT], conflict-free
+    uint32_t* const sstack = reinterpret_cast<uint32_t*>(pool + NS * PS_REC * NT);  // [SD][NT], conflict-free
     uint32_t nodes_saddr = 0u, prims_saddr = 0u;
     if constexpr (SCENE != 0) {
         float4* dst = reinterpret_cast<float4*>(sstack + SD * NT);
@@ -208,11 +285,14 @@ __global__ void __launch_bounds__(NT, (STATS || NT > 128) ? 1 : PS_MIN_BLOCKS) p
     uint32_t chunk_pixel = 0, chunk_sample = 0;  // (pixel, sample) of path chunk_next
     bool exhausted = false;
     unsigned int n_rays = 0;
+    // (scenes that need the general media sampler keep to the shade phase: with the out-of-line sampler inside it the chain
+    // phase would cost that kernel instance 480 B more spills)
+    const bool chain_on = CHAIN && MEDIA != MEDIA_GENERAL && S.clear_media != 0u && tune.chain_trig > 0 && !(MEDIA == MEDIA_ANY && S.media_general);  // warp-uniform
 
     for (;;) {
         // ---- (1) an idle lane starts traversing one of its ready paths
         if (tslot < 0) {
-            const int sl = slot_find(stat, ST_READY);
+            const int sl = slot_find<NS>(stat, ST_READY);
             if (sl >= 0) {
                 r.o = v3(POOL(sl, R_OX), POOL(sl, R_OY), POOL(sl, R_OZ)), r.d = v3(POOL(sl, R_DX), POOL(sl, R_DY), POOL(sl, R_DZ));
                 t_best = POOL(sl, R_T), hit = __float_as_int(POOL(sl, R_HIT)), origin_prim = __float_as_int(POOL(sl, R_ORIGIN));
@@ -224,11 +304,32 @@ __global__ void __launch_bounds__(NT, (STATS || NT > 128) ? 1 : PS_MIN_BLOCKS) p
             }
         }
         const bool trav = tslot >= 0;
-        const int s_done = slot_find(stat, ST_DONE);
-        const int s_work = s_done >= 0 ? s_done : (exhausted ? -1 : slot_find(stat, ST_EMPTY));
+        const int s_done = slot_find<NS>(stat, ST_DONE);
+        const int s_work = s_done >= 0 ? s_done : (exhausted ? -1 : slot_find<NS>(stat, ST_EMPTY));
         const unsigned int m_trav = __ballot_sync(0xffffffffu, trav);
         const unsigned int m_work = __ballot_sync(0xffffffffu, s_work >= 0);
-        if ((m_trav | m_work) == 0u) break;
+        int n_chain = 0;
+        if (CHAIN && chain_on) {
+#pragma unroll
+            for (int k = 0; k < NS; ++k) n_chain += __popc(__ballot_sync(0xffffffffu, slot_status(stat, k) == ST_CHAIN));
+        }
+        if ((m_trav | m_work) == 0u && n_chain == 0) break;
+
+        if (CHAIN && MEDIA != MEDIA_GENERAL && n_chain > 0 && (n_chain >= tune.chain_trig || (m_trav | m_work) == 0u)) {
+            // The registers of the traversal in flight must not stay live across this phase (80 registers: they would be
+            // spilled all over the traversal loop).  Ray, origin primitive and face are in the path's record anyway; the
+            // closest hit so far goes there too (what the record holds at the end of the traversal, only earlier), and the
+            // context is read back — node_ray recomputed — afterwards.  Only the cursor and the stack depth stay in registers.
+            const int sl = tslot >= 0 ? tslot : 0;
+            if (tslot >= 0) POOL(sl, R_T) = t_best, POOL(sl, R_HIT) = __int_as_float(hit);
+            const uint2 res = chain_phase<NT, NS, MEDIA == MEDIA_GENERAL ? MEDIA_FAST : MEDIA, STATS>(pool, S, P, (m_trav | m_work) == 0u ? 1 : tune.chain_min, stat, STATS ? st_ : nullptr);
+            stat = res.x, n_rays += res.y;
+            r.o = v3(POOL(sl, R_OX), POOL(sl, R_OY), POOL(sl, R_OZ)), r.d = v3(POOL(sl, R_DX), POOL(sl, R_DY), POOL(sl, R_DZ));
+            t_best = POOL(sl, R_T), hit = __float_as_int(POOL(sl, R_HIT)), origin_prim = __float_as_int(POOL(sl, R_ORIGIN));
+            origin_face = (int)((__float_as_uint(POOL(sl, R_FLAGS)) >> WF_FACE_SHIFT) & 7u);
+            nr = node_ray(r);
+            continue;
+        }
 
         if (m_work && (m_trav == 0u || __popc(m_work) >= tune.work || __popc(m_work & ~m_trav) >= tune.stall)) {
             // ================================================================ shade / regenerate phase
@@ -254,6 +355,9 @@ __global__ void __launch_bounds__(NT, (STATS || NT > 128) ? 1 : PS_MIN_BLOCKS) p
             // noise textures: one point at a time, all lanes on its 56 gradient terms
             {
                 unsigned int m_noise = __ballot_sync(0xffffffffu, req.tex >= 0);
+#ifdef RTB_AB_NO_NOISE  // timing A/B only (build flavor "nonoise"): how much of the kernel's time is the FOOTPRINT of this code (instruction cache)
+                m_noise = 0u;
+#endif
                 while (m_noise) {
                     PS_STAT(PSS_NOISE, 1)
                     const int src = __ffs((int)m_noise) - 1;
@@ -300,7 +404,14 @@ __global__ void __launch_bounds__(NT, (STATS || NT > 128) ? 1 : PS_MIN_BLOCKS) p
                         exhausted = true;
                         break;
                     }
-                    chunk_pixel = (uint32_t)(chunk_next % npix), chunk_sample = (uint32_t)P.sample_begin + (uint32_t)(chunk_next / npix);
+                    {  // (pixel, sample) of path chunk_next < 2^33: quotient through f64 (exact to +-1, then corrected) instead of the
+                       // 64-bit integer division routine — ~90 instructions that the instruction cache would carry for a rare step
+                        uint32_t q = (uint32_t)__double2ll_rz((double)(long long)chunk_next * P.inv_npix);
+                        long long rem = (long long)chunk_next - (long long)q * (long long)npix;
+                        if (rem < 0) q -= 1u, rem += npix;
+                        if (rem >= (long long)npix) q += 1u, rem -= npix;
+                        chunk_pixel = (uint32_t)rem, chunk_sample = (uint32_t)P.sample_begin + q;
+                    }
                     continue;
                 }
                 const unsigned int want = (unsigned int)__popc(m_need);
@@ -309,7 +420,7 @@ __global__ void __launch_bounds__(NT, (STATS || NT > 128) ? 1 : PS_MIN_BLOCKS) p
                 if (need && rank < take) {
                     uint32_t pixel = chunk_pixel + rank, sample = chunk_sample;
                     while (pixel >= npix) pixel -= npix, sample += 1u;
-                    wf_init_camera(cam, P, pixel, sample, s);
+                    wf_init_camera<FEAT>(cam, P, pixel, sample, s);
                     segment_next = 0;
                     alive = true, need = false;
                 }
@@ -321,9 +432,11 @@ __global__ void __launch_bounds__(NT, (STATS || NT > 128) ? 1 : PS_MIN_BLOCKS) p
             // survivors and fresh camera paths alike: media event of the new ray, then "ready"
             if (act) {
                 if (alive) {
+                    const int code_shaded = __float_as_int(s.D.y);  // the hit this path was shaded at (wf_shade_core leaves it; a fresh camera path: 0)
                     wf_presample_media<MEDIA>(S, P, s, segment_next);
                     rec_store<NT>(pool, s_work, s);
-                    stat = slot_set(stat, s_work, ST_READY);
+                    // a medium event of a clear medium followed by another one: the path hops on in the chain phase
+                    stat = slot_set(stat, s_work, (CHAIN && chain_on && wf_chain_eligible(S, code_shaded, s)) ? ST_CHAIN : ST_READY);
                 } else {
                     stat = slot_set(stat, s_work, ST_EMPTY);
                 }
@@ -410,7 +523,7 @@ __global__ void __launch_bounds__(NT, (STATS || NT > 128) ? 1 : PS_MIN_BLOCKS) p
                     } else {
                         q = load_prim(S.prims + i);
                     }
-                    if (q.meta & PRIM_MOVING) apply_motion(S, q, time_of_flags(__float_as_uint(POOL(tslot, R_FLAGS))));  // EXTENSION
+                    if ((FEAT & F_MOVING) && (q.meta & PRIM_MOVING)) apply_motion(S, q, time_of_flags(__float_as_uint(POOL(tslot, R_FLAGS))));  // EXTENSION
                     float t;
                     int face;
                     if (hit_prim(S, q, r, RTB_T_MIN, t_best, i == origin_prim, origin_face, t, face))
@@ -459,38 +572,69 @@ namespace {
 
 typedef void (*PersistFn)(DSceneView, DCamera, DRenderParams, PsCounters*, AccumFx*, unsigned long long*, unsigned int, unsigned long long*, PsTune);
 struct Variant {
-    int layout, smem_stack, threads, scene;
+    int layout, smem_stack, threads, scene, slots;
     PersistFn fn, fn_general, fn_stats;  // fn: scenes with <= 4 single-primitive media; fn_general: any media (rt_device.cuh: sample_media)
     const char* name;
 };
 // [fast-media instance, general-media instance, stats instance (decides at run time)]
-#define PS_INSTANCE(wide, sd, nt, scene) \
-    persist_kernel<false, wide, sd, nt, scene, MEDIA_FAST>, persist_kernel<false, wide, sd, nt, scene, MEDIA_GENERAL>, persist_kernel<true, wide, sd, nt, scene, MEDIA_ANY>
+#define PS_INSTANCE(wide, sd, nt, scene, ns, chain) \
+    persist_kernel<false, wide, sd, nt, scene, MEDIA_FAST, ns, chain, F_ALL>, persist_kernel<false, wide, sd, nt, scene, MEDIA_GENERAL, ns, false, F_ALL>, \
+        persist_kernel<true, wide, sd, nt, scene, MEDIA_ANY, ns, chain, F_ALL>
 // The kernel instances the library carries.  Measured on C4 (profiles/r2_ab_variants.txt): [1] is +1.6 % over [0], [2]
 // (one 768-thread block per SM instead of six 128-thread blocks: 5 KB more L1, one pool) another +1.8 %.
 // RTB_PS_EXPERIMENTS adds the rejected placements (stack levels or scene copies in shared memory: -2 ... -9 %, the L1
 // they take away costs more than the shared-memory latency wins) so that the A/B stays reproducible
 // (tools/experiments/build_experiments.sh); the product build does not carry them.
 const Variant kVariants[] = {
-    {2, 0, 128, 0, PS_INSTANCE(false, 0, 128, 0), "bvh2, 6 x 128 threads per SM"},  // north_star's 32-byte-node binary tree
-    {4, 0, 128, 0, PS_INSTANCE(true, 0, 128, 0), "bvh4, 6 x 128 threads per SM"},
-    {4, 0, 768, 0, PS_INSTANCE(true, 0, 768, 0), "bvh4, 1 x 768 threads per SM"},
+    {2, 0, 128, 0, 2, PS_INSTANCE(false, 0, 128, 0, 2, false), "bvh2, 6 x 128 threads per SM"},  // north_star's 32-byte-node binary tree
+    {4, 0, 128, 0, 2, PS_INSTANCE(true, 0, 128, 0, 2, false), "bvh4, 6 x 128 threads per SM"},
+    {4, 0, 768, 0, 2, PS_INSTANCE(true, 0, 768, 0, 2, false), "bvh4, 1 x 768 threads per SM"},
 #ifdef RTB_PS_EXPERIMENTS
-    {4, 0, 640, 0, PS_INSTANCE(true, 0, 640, 0), "bvh4, 1 x 640 threads per SM (96 registers)"},
-    {4, 0, 896, 0, PS_INSTANCE(true, 0, 896, 0), "bvh4, 1 x 896 threads per SM (72 registers)"},
-    {4, 0, 1024, 0, PS_INSTANCE(true, 0, 1024, 0), "bvh4, 1 x 1024 threads per SM (64 registers)"},
-    {4, 8, 128, 0, PS_INSTANCE(true, 8, 128, 0), "bvh4, 6 x 128 threads, 8 stack levels in shared memory"},
-    {4, 0, 768, 1, PS_INSTANCE(true, 0, 768, 1), "bvh4, 1 x 768 threads, nodes in shared memory"},
-    {4, 0, 768, 2, PS_INSTANCE(true, 0, 768, 2), "bvh4, 1 x 768 threads, primitives in shared memory"},
-    {4, 0, 768, 3, PS_INSTANCE(true, 0, 768, 3), "bvh4, 1 x 768 threads, nodes + primitives in shared memory"},
-    {4, 0, 640, 3, PS_INSTANCE(true, 0, 640, 3), "bvh4, 1 x 640 threads, nodes + primitives in shared memory"},
+    {4, 0, 640, 0, 2, PS_INSTANCE(true, 0, 640, 0, 2, false), "bvh4, 1 x 640 threads per SM (96 registers)"},
+    {4, 0, 896, 0, 2, PS_INSTANCE(true, 0, 896, 0, 2, false), "bvh4, 1 x 896 threads per SM (72 registers)"},
+    {4, 0, 1024, 0, 2, PS_INSTANCE(true, 0, 1024, 0, 2, false), "bvh4, 1 x 1024 threads per SM (64 registers)"},
+    {4, 8, 128, 0, 2, PS_INSTANCE(true, 8, 128, 0, 2, false), "bvh4, 6 x 128 threads, 8 stack levels in shared memory"},
+    {4, 0, 768, 1, 2, PS_INSTANCE(true, 0, 768, 1, 2, false), "bvh4, 1 x 768 threads, nodes in shared memory"},
+    {4, 0, 768, 2, 2, PS_INSTANCE(true, 0, 768, 2, 2, false), "bvh4, 1 x 768 threads, primitives in shared memory"},
+    {4, 0, 768, 3, 2, PS_INSTANCE(true, 0, 768, 3, 2, false), "bvh4, 1 x 768 threads, nodes + primitives in shared memory"},
+    {4, 0, 640, 3, 2, PS_INSTANCE(true, 0, 640, 3, 2, false), "bvh4, 1 x 640 threads, nodes + primitives in shared memory"},
 #endif
+    // The chain phase (wf_chain_step) as an opt-in instance, RT_PS_CHAIN=1: it removes 7 % of C4's warp instructions and
+    // still loses 10 %, because the instructions the kernel then executes per frame (39 KB) no longer fit the SM's 32 KB
+    // instruction cache (profiles/r2_chain_phase.txt) — carrying its code in the default instance cost 13 % even switched off.
+    {4, 0, 768, 0, 2, PS_INSTANCE(true, 0, 768, 0, 2, true), "bvh4, 1 x 768 threads per SM, chain phase for clear media"},
 };
 const int kNumVariants = (int)(sizeof(kVariants) / sizeof(kVariants[0]));
-static_assert(sizeof(kVariants) / sizeof(kVariants[0]) <= PS_VARIANTS, "PersistState::blocks is too small");
+
+// Feature-specialised instances of the product variant (bvh4, 1 x 768 threads, fast media): the first whose mask covers the
+// scene's features is launched, so that the kernel holds no code the scene cannot reach.  Not a dispatch on speed of the
+// tests themselves: what counts is that the ~31 KB of instructions final_scene executes per frame lie contiguous and
+// below the 32 KB of the SM's instruction cache (RT_PS_FEAT=0 launches the generic instance).
+struct FeatInstance {
+    uint32_t mask;
+    PersistFn fn;
+    const char* name;
+};
+#define PS_FEAT_INSTANCE(mask) mask, persist_kernel<false, true, 0, 768, 0, MEDIA_FAST, 2, false, mask>
+constexpr uint32_t kFeatSpheres = F_SPHERE | F_BIG;                                                           // random (C1, C2), simple
+constexpr uint32_t kFeatBoxes = F_BOX | F_INSTBOX | F_INSTANCE | F_MEDIA | F_BOXMEDIA;                        // cornell_box, cornell_smoke (C3)
+constexpr uint32_t kFeatFinal = F_SPHERE | F_BOX | F_INSTANCE | F_BIG | F_MEDIA | F_NOISE | F_IMAGE;          // final_scene (C4, C5)
+const FeatInstance kFeatInstances[] = {
+    {PS_FEAT_INSTANCE(kFeatSpheres), "spheres"},
+    {PS_FEAT_INSTANCE(kFeatBoxes), "boxes, instances, box media"},
+    {PS_FEAT_INSTANCE(kFeatFinal), "spheres, world-space boxes, sphere media, noise and image textures"},
+};
+PersistFn pick_feature_instance(const RtScene* s, int vi, PersistFn generic) {
+    if (vi != PS_DEFAULT_VARIANT || s->view.media_general) return generic;
+    if (const char* e = getenv("RT_PS_FEAT"))
+        if (atoi(e) == 0) return generic;
+    for (const FeatInstance& f : kFeatInstances)
+        if ((s->flat.features & ~f.mask) == 0u) return f.fn;
+    return generic;
+}
 
 size_t variant_smem(const Variant& V, const RtScene* s) {
-    size_t bytes = (size_t)PS_SLOTS * PS_REC * V.threads * sizeof(float) + (size_t)V.smem_stack * V.threads * sizeof(uint32_t);
+    size_t bytes = (size_t)V.slots * PS_REC * V.threads * sizeof(float) + (size_t)V.smem_stack * V.threads * sizeof(uint32_t);
     if (V.scene & PS_SCENE_NODES) bytes += s->flat.nodes4.size() * sizeof(DNode4);
     if (V.scene & PS_SCENE_PRIMS) bytes += s->flat.prims.size() * sizeof(DPrim);
     return bytes;
@@ -505,6 +649,8 @@ int pick_variant(const RtScene* s, const RtParams* p) {
     if (layout == 2) return 0;
     int vi = PS_DEFAULT_VARIANT;
     if (const char* e = getenv("RT_PS_VARIANT")) vi = std::max(1, std::min(kNumVariants - 1, atoi(e)));
+    if (const char* e = getenv("RT_PS_CHAIN"))
+        if (atoi(e) != 0 && s->flat.clear_media != 0u) vi = kNumVariants - 1;
     if (variant_smem(kVariants[vi], s) > PS_MAX_SMEM) vi = 1;  // the scene copy does not fit beside the path pool
     return vi;
 }
@@ -520,7 +666,8 @@ void persist_preload(const RtScene* s) {
     p.max_depth = 1;
     const Variant& V = kVariants[pick_variant(s, &p)];
     cudaFuncAttributes fa;
-    if (cudaFuncGetAttributes(&fa, s->view.media_general ? V.fn_general : V.fn) != cudaSuccess) cudaGetLastError();
+    const int vi = pick_variant(s, &p);
+    if (cudaFuncGetAttributes(&fa, s->view.media_general ? V.fn_general : pick_feature_instance(s, vi, V.fn)) != cudaSuccess) cudaGetLastError();
 }
 
 int launch_persist(RtScene* s, const DCamera& cam, const RtParams* p, int begin, int count, AccumFx* d_accum, cudaStream_t stream, RtProgressFn cb,
@@ -537,8 +684,9 @@ int launch_persist(RtScene* s, const DCamera& cam, const RtParams* p, int begin,
     const Variant& V = kVariants[vi];
     const size_t smem = variant_smem(V, s);
     const int NT = V.threads;
-    const PersistFn kernel = s->view.media_general ? V.fn_general : V.fn;
-    if (w->blocks[vi] == 0) {
+    const PersistFn kernel = s->view.media_general ? V.fn_general : pick_feature_instance(s, vi, V.fn);
+    const void* const key = getenv("RT_PS_STATS") ? (const void*)V.fn_stats : (const void*)kernel;
+    if (w->blocks.find(key) == w->blocks.end()) {
         int per_sm = 0, sms = 0;
         // (the statistics instance only when it will be launched: touching a kernel makes the driver load it, which a 3 ms job notices)
         CU_TRY(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
@@ -554,7 +702,7 @@ int launch_persist(RtScene* s, const DCamera& cam, const RtParams* p, int begin,
         if (const char* e = getenv("RT_PS_CARVEOUT")) percent = atoi(e);
         CU_TRY(cudaFuncSetAttribute(kernel, cudaFuncAttributePreferredSharedMemoryCarveout, percent));
         CU_TRY(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, s->device));
-        w->blocks[vi] = per_sm * std::max(1, sms);  // persistent: exactly what is co-resident
+        w->blocks[key] = per_sm * std::max(1, sms);  // persistent: exactly what is co-resident
     }
     const unsigned long long npix = (unsigned long long)p->width * p->height;
     // one launch = up to 2^29 camera paths when progress is reported (a quarter of a second on C4), 2^33 otherwise: every
@@ -565,13 +713,15 @@ int launch_persist(RtScene* s, const DCamera& cam, const RtParams* p, int begin,
         int samples = std::min(count - done, samples_per_launch);
         unsigned long long total = npix * (unsigned long long)samples;
         DRenderParams P = device_params(p, begin + done, 1, 1);
-        int blocks = (int)std::min<unsigned long long>((unsigned long long)w->blocks[vi], (total + 2 * NT - 1) / (2 * NT));
+        int blocks = (int)std::min<unsigned long long>((unsigned long long)w->blocks[key], (total + 2 * NT - 1) / (2 * NT));
         // small jobs: smaller reservations so that every warp gets work
         unsigned long long per_warp = total / ((unsigned long long)blocks * (NT / 32) * 4ull);
         unsigned int chunk = (unsigned int)std::min<unsigned long long>(PS_CHUNK, std::max<unsigned long long>(32ull, per_warp));
         chunk = (unsigned int)std::min<unsigned long long>(chunk, std::max<unsigned long long>(1ull, npix));
         ps_reset_kernel<<<1, 1, 0, stream>>>(w->ctr, total);
-        PsTune tune = {PS_WORK, PS_STALL, PS_LEAVE, PS_MIN_DESCEND};
+        PsTune tune = {PS_WORK, PS_STALL, PS_LEAVE, PS_MIN_DESCEND, PS_CHAIN_TRIG, PS_CHAIN_MIN};
+        if (const char* e = getenv("RT_PS_CHAIN_TRIG")) tune.chain_trig = atoi(e);
+        if (const char* e = getenv("RT_PS_CHAIN_MIN")) tune.chain_min = std::max(1, atoi(e));
         if (const char* e = getenv("RT_PS_WORK")) tune.work = atoi(e);
         if (const char* e = getenv("RT_PS_STALL")) tune.stall = atoi(e);
         if (const char* e = getenv("RT_PS_LEAVE")) tune.leave = atoi(e);
@@ -586,7 +736,8 @@ int launch_persist(RtScene* s, const DCamera& cam, const RtParams* p, int begin,
             CU_TRY(cudaStreamSynchronize(stream));
             cudaFree(d_stats);
             static const char* names[PSS_COUNT] = {"shade_phases", "shade_act_lanes", "shade_done_lanes", "shade_onpark_lanes", "ext_phases", "inner_iters",
-                                                   "inner_lanes", "leaf_steps", "leaf_lanes", "leaf_prims", "ext_rounds", "ext_trav_lanes", "noise_evals"};
+                                                   "inner_lanes", "leaf_steps", "leaf_lanes", "leaf_prims", "ext_rounds", "ext_trav_lanes", "noise_evals",
+                                                   "chain_phases", "chain_records", "chain_iters", "chain_lanes", "chain_parked"};
             fprintf(stderr, "persist stats [%s] (%llu paths):", V.name, total);
             for (int k = 0; k < PSS_COUNT; ++k) fprintf(stderr, " %s=%llu", names[k], h[k]);
             fprintf(stderr, "\n");

@@ -139,8 +139,29 @@ struct DImage {
     int32_t width, height;
 };
 
+// ---- scene features.  A device function asks SV::feat (SV = the type of the scene view it was handed) before its run-time
+// test, so that a kernel instantiated for SceneViewF<mask> carries no code for what the scene does not contain.  This is
+// about instruction FOOTPRINT, not about the tests: the persistent kernel executes ~31 KB of instructions per frame on
+// final_scene against a 32 KB instruction cache, and code that a scene never runs sits between the lines it does run.
+enum : uint32_t {
+    F_BOX = 1u,          // box / rect primitives
+    F_INSTBOX = 2u,      // ... under a Translate / Rotate chain (tested in object space)
+    F_INSTANCE = 4u,     // any primitive under a Translate / Rotate chain (normals re-face-forwarded per wrapper)
+    F_MOVING = 8u,       // EXTENSION: moving spheres
+    F_BIG = 16u,         // spheres of |r| >= RTB_BIG_SPHERE_RADIUS (f64 roots next to their surface)
+    F_MEDIA = 32u,       // constant media
+    F_BOXMEDIA = 64u,    // ... with a box boundary
+    F_CHECKER = 128u,
+    F_NOISE = 256u,
+    F_IMAGE = 512u,
+    F_SPHERE = 1024u,    // sphere primitives
+    F_UVBOX = 2048u,     // a box / rect whose texture reads (u, v) (an image below its material)
+    F_ALL = 0xFFFFFFFFu,
+};
+
 // what every kernel receives by value
 struct DSceneView {
+    static constexpr uint32_t feat = F_ALL;
     const DNode* nodes;
     const DNode4* nodes4;  // 4-wide collapse of `nodes` (nullptr when the scene exceeds the 16-bit links)
     const DPrim* prims;
@@ -156,9 +177,15 @@ struct DSceneView {
     const float* moving;  // EXTENSION: n x 4 floats, c1 - c0 of every moving sphere
     int32_t n_nodes, n_nodes4, n_prims, n_media, n_perlin;
     int32_t media_general;  // more than four media, or a boundary of several primitives: the out-of-line sampler
+    uint32_t clear_media;   // bit m: nothing but medium m inside its (convex, single-primitive) boundary — see wf_chain_step
     int32_t bg_kind;
     float bg_top[3];
     float bg_bottom[3];
+};
+
+template <uint32_t F>
+struct SceneViewF : DSceneView {
+    static constexpr uint32_t feat = F;
 };
 
 struct DRenderParams {
@@ -170,6 +197,7 @@ struct DRenderParams {
     int32_t tiles_x, tiles_y; // 8x4 pixel tiles
     uint32_t seed_lo, seed_hi;
     float inv_wm1, inv_hm1;   // 1/(W-1), 1/(H-1)  (raytrace.rs:191-192)
+    double inv_npix;          // 1/(W*H): path number -> (pixel, sample) without a 64-bit integer division (rt_persist.cu)
 };
 
 }  // namespace rtb

@@ -34,6 +34,7 @@ static void make_view(EmulScene& e) {
     v.n_perlin = (int)(f.perlin_vec.size() / (4 * RTB_PERLIN_POINTS));
     v.media_general = f.media.size() > 4 ? 1 : 0;
     for (const auto& m : f.media) v.media_general |= m.count > 1 ? 1 : 0;
+    v.clear_media = f.clear_media;
     v.bg_kind = f.bg_kind;
     for (int k = 0; k < 3; ++k) v.bg_top[k] = f.bg_top[k], v.bg_bottom[k] = f.bg_bottom[k];
 }
@@ -151,6 +152,70 @@ uint64_t emul_render(void* h, const RtCamera* cam, const RtParams* p, int32_t th
     worker();
     for (auto& t : pool) t.join();
     return rays.load();
+}
+
+uint32_t emul_clear_media(void* h) { return ((EmulScene*)h)->flat.clear_media; }
+
+// The wavefront slot functions (wf_init_pixel_sample, closest hit, wf_shade) driven path by path on host threads, as the
+// persistent kernel drives them — with `use_chain`, paths inside a clear medium advance with wf_chain_step instead of a
+// surface search + wf_shade, as in the kernel's chain phase.  counters[0] = rays, counters[1] = chain steps.
+void emul_render_slots(void* h, const RtCamera* cam, const RtParams* p, int32_t threads, int32_t use_chain, uint64_t* accum, uint64_t* counters) {
+    EmulScene* e = (EmulScene*)h;
+    const DSceneView& S = e->view;
+    DCamera dc;
+    make_camera(*cam, dc);
+    int count = p->sample_count > 0 ? p->sample_count : p->samples_per_pixel;
+    DRenderParams P = make_params(p, 1, 1);
+    std::atomic<int> next(0);
+    std::atomic<uint64_t> rays(0), steps(0);
+    if (threads <= 0) threads = (int)std::thread::hardware_concurrency();
+    auto worker = [&]() {
+        uint64_t local_rays = 0, local_steps = 0;
+        for (;;) {
+            int j = next.fetch_add(1);
+            if (j >= p->height) break;
+            for (int i = 0; i < p->width; ++i) {
+                AccumFx sum[3] = {0, 0, 0};
+                const uint32_t pixel = (uint32_t)(j * p->width + i);
+                for (int k = 0; k < count && p->max_depth > 0; ++k) {
+                    WfSlot s;
+                    wf_init_pixel_sample(S, dc, P, pixel, (uint32_t)(p->sample_begin + k), s);
+                    bool chain = false;
+                    for (;;) {
+                        local_rays += 1;
+                        if (chain) {
+                            local_steps += 1;
+                            const int rc = wf_chain_step(S, P, s);
+                            if (rc == 0) break;  // Color::ZERO
+                            chain = rc == 1;
+                            continue;
+                        }
+                        Ray r;
+                        r.o = v3(s.A.x, s.A.y, s.A.z), r.d = v3(s.B.x, s.B.y, s.B.z);
+                        const uint32_t flags = as_uint(s.B.w);
+                        float t = s.D.x;
+                        int prim, face;
+                        closest_hit(S, r, RTB_T_MIN, t, (int)as_uint(s.D.z), (int)((flags >> WF_FACE_SHIFT) & 7u), t, prim, face, time_of_flags(flags));
+                        if (prim >= 0) s.D.x = t, s.D.y = as_float((uint32_t)(prim | (face << 24)));
+                        const int code = (int)as_uint(s.D.y);
+                        V3 radiance;
+                        if (!wf_shade(S, P, s, radiance)) {
+                            sum[0] += radiance_fixed(radiance.x), sum[1] += radiance_fixed(radiance.y), sum[2] += radiance_fixed(radiance.z);
+                            break;
+                        }
+                        chain = use_chain != 0 && wf_chain_eligible(S, code, s);
+                    }
+                }
+                for (int k = 0; k < 3; ++k) accum[3 * (size_t)pixel + k] = sum[k];
+            }
+        }
+        rays += local_rays, steps += local_steps;
+    };
+    std::vector<std::thread> pool;
+    for (int t = 1; t < threads; ++t) pool.emplace_back(worker);
+    worker();
+    for (auto& t : pool) t.join();
+    counters[0] = rays.load(), counters[1] = steps.load();
 }
 
 }  // extern "C"

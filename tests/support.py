@@ -95,6 +95,9 @@ def emul():
         L.emul_unit_ball.argtypes = [C.c_void_p, C.c_int64, C.c_void_p]
         L.emul_render.restype = C.c_uint64
         L.emul_render.argtypes = [C.c_void_p, C.POINTER(abi.RtCamera), C.POINTER(abi.RtParams), C.c_int32, C.c_void_p]
+        L.emul_clear_media.restype = C.c_uint32
+        L.emul_clear_media.argtypes = [C.c_void_p]
+        L.emul_render_slots.argtypes = [C.c_void_p, C.POINTER(abi.RtCamera), C.POINTER(abi.RtParams), C.c_int32, C.c_int32, C.c_void_p, C.c_void_p]
         _emul = L
     return _emul
 
@@ -216,6 +219,21 @@ class EmulScene:
         if fixed:
             return accum, rays
         return (accum.astype(np.float64) / abi.RT_ACCUM_FIXED_ONE).astype(np.float32), rays
+
+    @property
+    def clear_media(self):
+        return int(emul().emul_clear_media(self.h))
+
+    def render_slots(self, cam, width, height, spp, chain, max_depth=50, seed=42, threads=0):
+        """the wavefront slot functions driven path by path (fixed-point sums, rays, chain steps); chain=True advances
+        paths inside a clear medium with wf_chain_step as the persistent kernel's chain phase does"""
+        p = abi.RtParams()
+        p.width, p.height, p.samples_per_pixel, p.max_depth = width, height, spp, max_depth
+        p.seed, p.sample_begin, p.sample_count = seed, 0, spp
+        accum = np.zeros((height, width, 3), dtype=np.uint64)
+        counters = np.zeros(2, dtype=np.uint64)
+        emul().emul_render_slots(self.h, C.byref(cam.c), C.byref(p), threads, 1 if chain else 0, accum.ctypes.data, counters.ctypes.data)
+        return accum, int(counters[0]), int(counters[1])
 
     def close(self):
         if self.h:
