@@ -22,7 +22,7 @@ MATH = ["-ftz=true", "-prec-div=false", "-prec-sqrt=false"]
 FLAVORS = {"": MATH, "fast": ["--use_fast_math"], "precise": [],
            "exp": MATH + ["-DRTB_PS_EXPERIMENTS"],  # + the rejected kernel placements of rt_persist.cu (tools/experiments/)
            "floatred": MATH + ["-DRTB_AB_FLOAT_RED"],
-           "nonoise": MATH + ["-DRTB_AB_NO_NOISE"]}  # noise textures answer 1: what their ~3 KB of instructions cost the instruction cache  # cost of the 64-bit fixed-point REDs against 32-bit float REDs
+           "nonoise": MATH + ["-DRTB_AB_NO_NOISE"]}
 FLAVOR = os.environ.get("RT_BUILD_FLAVOR", "")
 if FLAVOR:
     OUT = os.path.join(HERE, "librt_b200_%s.so" % FLAVOR)

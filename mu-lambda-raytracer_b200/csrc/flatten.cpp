@@ -423,7 +423,6 @@ class Flattener {
                 return;
             }
             f |= sphere ? F_SPHERE : F_BOX;
-            if (!sphere && q.mat >= 0 && q.mat < (int)out.mats.size() && out.mats[q.mat].tex >= 0 && out.texs[out.mats[q.mat].tex].needs_uv) f |= F_UVBOX;
             if (inst) f |= F_INSTANCE | (sphere ? 0u : F_INSTBOX);
         };
         for (const DPrim& q : out.prims) prim_bits(q, false);

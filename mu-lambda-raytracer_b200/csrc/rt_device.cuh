@@ -891,7 +891,7 @@ RTB_DEV void surface_at(const SV& S, const PrimRec& P, const Ray& r, float t, in
             else if (k == 1) s.p.y = plane;
             else s.p.z = plane;
         }
-        if ((SV::feat & F_UVBOX) && want_uv) {
+        if (want_uv) {  // (a feature bit for "no box reads (u, v)" was tried: 56 instructions less and 32 B more spills, -3.5 %)
             Ray ro = to_object_space(S, inst, r);
             V3 po = ro.o + t * ro.d;
             int a0 = k == 0 ? 1 : 0, a1 = k == 2 ? 1 : 2;

@@ -215,9 +215,9 @@ __device__ __forceinline__ uint2 chain_phase(float* pool, const SV& S, const DRe
 #define PS_SCENE_NODES 1
 #define PS_SCENE_PRIMS 2
 template <bool STATS, bool WIDE, int SD, int NT, int SCENE, int MEDIA, int NS, bool CHAIN, uint32_t FEAT>
-__global__ void __launch_bounds__(NT, (STATS || NT > 128) ? 1 : PS_MIN_BLOCKS) persist_kernel(DSceneView S_, DCamera cam, DRenderParams P, PsCounters* __restrict__ ctr,
-                                                             AccumFx* __restrict__ accum, unsigned long long* __restrict__ rays_out,
-                                                             unsigned int chunk_size, unsigned long long* __restrict__ stats, PsTune tune) {
+__device__ __forceinline__ void persist_body(const DSceneView& S_, const DCamera& cam, const DRenderParams& P, PsCounters* __restrict__ ctr,
+                                             AccumFx* __restrict__ accum, unsigned long long* __restrict__ rays_out, unsigned int chunk_size,
+                                             unsigned long long* __restrict__ stats, const PsTune& tune) {
     const SceneViewF<FEAT>& S = static_cast<const SceneViewF<FEAT>&>(S_);  // same record; SV::feat = what the scene can contain (rt_types.h)
     unsigned int st_[PSS_COUNT];
     if (STATS)
@@ -558,6 +558,13 @@ __global__ void __launch_bounds__(NT, (STATS || NT > 128) ? 1 : PS_MIN_BLOCKS) p
 #undef PS_STAT
 }
 
+template <bool STATS, bool WIDE, int SD, int NT, int SCENE, int MEDIA, int NS, bool CHAIN, uint32_t FEAT>
+__global__ void __launch_bounds__(NT, (STATS || NT > 128) ? 1 : PS_MIN_BLOCKS) persist_kernel(DSceneView S, DCamera cam, DRenderParams P, PsCounters* __restrict__ ctr,
+                                                             AccumFx* __restrict__ accum, unsigned long long* __restrict__ rays_out,
+                                                             unsigned int chunk_size, unsigned long long* __restrict__ stats, PsTune tune) {
+    persist_body<STATS, WIDE, SD, NT, SCENE, MEDIA, NS, CHAIN, FEAT>(S, cam, P, ctr, accum, rays_out, chunk_size, stats, tune);
+}
+
 // ---------------------------------------------------------------------------------------------------------------
 void free_persist(RtScene* s) {
     if (!s->ps) return;
@@ -610,26 +617,32 @@ const int kNumVariants = (int)(sizeof(kVariants) / sizeof(kVariants[0]));
 // scene's features is launched, so that the kernel holds no code the scene cannot reach.  Not a dispatch on speed of the
 // tests themselves: what counts is that the ~31 KB of instructions final_scene executes per frame lie contiguous and
 // below the 32 KB of the SM's instruction cache (RT_PS_FEAT=0 launches the generic instance).
+// (Registers: 24 warps = 6 per SM sub-partition leave 80 registers a thread and 24 - 52 B of spills; 23 or 22 warps do not
+// help, a sub-partition still holds 6 of them; 20 warps at 96 registers measured -2.6 %, profiles/r2_ab_variants.txt run i.)
 struct FeatInstance {
     uint32_t mask;
+    int threads;
     PersistFn fn;
     const char* name;
 };
-#define PS_FEAT_INSTANCE(mask) mask, persist_kernel<false, true, 0, 768, 0, MEDIA_FAST, 2, false, mask>
+#define PS_FEAT_INSTANCE(mask, nt) mask, nt, persist_kernel<false, true, 0, nt, 0, MEDIA_FAST, 2, false, mask>
 constexpr uint32_t kFeatSpheres = F_SPHERE | F_BIG;                                                           // random (C1, C2), simple
 constexpr uint32_t kFeatBoxes = F_BOX | F_INSTBOX | F_INSTANCE | F_MEDIA | F_BOXMEDIA;                        // cornell_box, cornell_smoke (C3)
 constexpr uint32_t kFeatFinal = F_SPHERE | F_BOX | F_INSTANCE | F_BIG | F_MEDIA | F_NOISE | F_IMAGE;          // final_scene (C4, C5)
 const FeatInstance kFeatInstances[] = {
-    {PS_FEAT_INSTANCE(kFeatSpheres), "spheres"},
-    {PS_FEAT_INSTANCE(kFeatBoxes), "boxes, instances, box media"},
-    {PS_FEAT_INSTANCE(kFeatFinal), "spheres, world-space boxes, sphere media, noise and image textures"},
+    {PS_FEAT_INSTANCE(kFeatSpheres, 768), "spheres"},
+    {PS_FEAT_INSTANCE(kFeatBoxes, 768), "boxes, instances, box media"},
+    {PS_FEAT_INSTANCE(kFeatFinal, 768), "spheres, world-space boxes, sphere media, noise and image textures"},
 };
-PersistFn pick_feature_instance(const RtScene* s, int vi, PersistFn generic) {
+PersistFn pick_feature_instance(const RtScene* s, int vi, PersistFn generic, int* threads) {
     if (vi != PS_DEFAULT_VARIANT || s->view.media_general) return generic;
     if (const char* e = getenv("RT_PS_FEAT"))
         if (atoi(e) == 0) return generic;
     for (const FeatInstance& f : kFeatInstances)
-        if ((s->flat.features & ~f.mask) == 0u) return f.fn;
+        if ((s->flat.features & ~f.mask) == 0u) {
+            *threads = f.threads;
+            return f.fn;
+        }
     return generic;
 }
 
@@ -667,7 +680,8 @@ void persist_preload(const RtScene* s) {
     const Variant& V = kVariants[pick_variant(s, &p)];
     cudaFuncAttributes fa;
     const int vi = pick_variant(s, &p);
-    if (cudaFuncGetAttributes(&fa, s->view.media_general ? V.fn_general : pick_feature_instance(s, vi, V.fn)) != cudaSuccess) cudaGetLastError();
+    int nt = V.threads;
+    if (cudaFuncGetAttributes(&fa, s->view.media_general ? V.fn_general : pick_feature_instance(s, vi, V.fn, &nt)) != cudaSuccess) cudaGetLastError();
 }
 
 int launch_persist(RtScene* s, const DCamera& cam, const RtParams* p, int begin, int count, AccumFx* d_accum, cudaStream_t stream, RtProgressFn cb,
@@ -682,9 +696,9 @@ int launch_persist(RtScene* s, const DCamera& cam, const RtParams* p, int begin,
     PersistState* w = s->ps;
     const int vi = pick_variant(s, p);
     const Variant& V = kVariants[vi];
-    const size_t smem = variant_smem(V, s);
-    const int NT = V.threads;
-    const PersistFn kernel = s->view.media_general ? V.fn_general : pick_feature_instance(s, vi, V.fn);
+    int NT = V.threads;
+    const PersistFn kernel = s->view.media_general ? V.fn_general : pick_feature_instance(s, vi, V.fn, &NT);
+    const size_t smem = variant_smem(V, s) / V.threads * NT;  // (every term of it is per thread for the variant feature instances exist for)
     const void* const key = getenv("RT_PS_STATS") ? (const void*)V.fn_stats : (const void*)kernel;
     if (w->blocks.find(key) == w->blocks.end()) {
         int per_sm = 0, sms = 0;

@@ -155,7 +155,6 @@ enum : uint32_t {
     F_NOISE = 256u,
     F_IMAGE = 512u,
     F_SPHERE = 1024u,    // sphere primitives
-    F_UVBOX = 2048u,     // a box / rect whose texture reads (u, v) (an image below its material)
     F_ALL = 0xFFFFFFFFu,
 };
 
