@@ -374,26 +374,29 @@ RTB_DEV Ray to_object_space(const SV& S, int inst, const Ray& r) {
 
 // slab crossings of an object-space box; `origin_face` (axis | side << 2, or -1) pins the plane the ray
 // starts on to t = 0 exactly, which is what f64 gives the reference for a ray leaving that face.
+// One axis of it.  Scalars on purpose: with lo[3] / hi[3] arrays the compiler turned the pinning test into dynamically
+// indexed loads and kept the arrays in LOCAL memory — 4 stores and 6 loads per box test in the hottest leaf path.
+RTB_DEV void box_axis(int k, float lo, float hi, float o, float d, int pin, int side, float& t_enter, float& t_exit, int& face_enter, int& face_exit) {
+    float inv = 1.0f / d;
+    float a = lo - o, b = hi - o;
+    if (pin == k) {
+        if (side) b = 0.0f;
+        else a = 0.0f;
+        if (lo == hi) a = b = 0.0f;  // a rect: both "sides" are the one plane
+    }
+    float ta = a * inv, tb = b * inv;
+    float tn = fminf(ta, tb), tf = fmaxf(ta, tb);  // fminf/fmaxf drop the NaN of 0 * inf
+    bool neg = d < 0.0f;
+    if (tn > t_enter) t_enter = tn, face_enter = k | ((neg ? 1 : 0) << 2);
+    if (tf < t_exit) t_exit = tf, face_exit = k | ((neg ? 0 : 1) << 2);
+}
 RTB_DEV bool box_slabs(const PrimRec& p, const Ray& r, int origin_face, float& t_enter, float& t_exit, int& face_enter, int& face_exit) {
-    float lo[3] = {p.v0, p.v1, p.v2}, hi[3] = {p.v3, p.v4, p.v5};
-    float o[3] = {r.o.x, r.o.y, r.o.z}, d[3] = {r.d.x, r.d.y, r.d.z};
     t_enter = -RTB_INF, t_exit = RTB_INF;
     face_enter = 0, face_exit = 0;
-#pragma unroll
-    for (int k = 0; k < 3; ++k) {
-        float inv = 1.0f / d[k];
-        float a = lo[k] - o[k], b = hi[k] - o[k];
-        if (origin_face >= 0 && (origin_face & 3) == k) {
-            if (origin_face >> 2) b = 0.0f;
-            else a = 0.0f;
-            if (lo[k] == hi[k]) a = b = 0.0f;  // a rect: both "sides" are the one plane
-        }
-        float ta = a * inv, tb = b * inv;
-        float tn = fminf(ta, tb), tf = fmaxf(ta, tb);  // fminf/fmaxf drop the NaN of 0 * inf
-        bool neg = d[k] < 0.0f;
-        if (tn > t_enter) t_enter = tn, face_enter = k | ((neg ? 1 : 0) << 2);
-        if (tf < t_exit) t_exit = tf, face_exit = k | ((neg ? 0 : 1) << 2);
-    }
+    const int pin = origin_face >= 0 ? (origin_face & 3) : -1, side = origin_face >> 2;
+    box_axis(0, p.v0, p.v3, r.o.x, r.d.x, pin, side, t_enter, t_exit, face_enter, face_exit);
+    box_axis(1, p.v1, p.v4, r.o.y, r.d.y, pin, side, t_enter, t_exit, face_enter, face_exit);
+    box_axis(2, p.v2, p.v5, r.o.z, r.d.z, pin, side, t_enter, t_exit, face_enter, face_exit);
     return t_enter <= t_exit;
 }
 
@@ -742,7 +745,8 @@ RTB_DEV void sample_media(const SV& S, const Ray& r, float tmin, const PathRng& 
         float t1, t2;
         if (!medium_interval(S, b, r, tmin, t_best, t1, t2)) continue;
         float inside = (t2 - t1) * len;
-        float dist = tail.x * fast_log(u[m]);  // neg_inv_density * ln(U)
+        const float um = m == 0 ? u[0] : (m == 1 ? u[1] : (m == 2 ? u[2] : u[3]));  // (u[m] would put the array in local memory)
+        float dist = tail.x * fast_log(um);  // neg_inv_density * ln(U)
         if (dist > inside) continue;
         t_best = t1 + dist / len;
         medium_best = m;
