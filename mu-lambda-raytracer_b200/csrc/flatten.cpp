@@ -371,8 +371,8 @@ class Flattener {
     // whole segment stays inside), hence the persistent kernel advances such paths from event to event without a
     // surface search (rt_persist.cu, chain phase).  Conservative test on the primitives as emitted (before the BVH build
     // reorders them): a surface primitive disqualifies the medium when its world box reaches into the interior of the
-    // boundary's world box — for a spherical boundary: into the ball — unless it is a sphere around the same centre that
-    // is at least as large (the boundary itself, added as a glass shell: final_scene, worlds.rs:430-437).
+    // boundary's world box — for a spherical boundary: into the ball; a sphere is tested exactly against it, so that the
+    // boundary itself, added to the world as a glass shell (final_scene, worlds.rs:430-437), does not count.
     std::vector<Box3> media_box;
     void find_clear_media() {
         out.clear_media = 0u;
@@ -400,7 +400,11 @@ class Flattener {
                     }
                     if (d2 >= r * r) continue;
                     const bool q_ball = (q.meta & PRIM_KIND_MASK) == PRIM_SPHERE && !(q.meta & PRIM_MOVING);
-                    if (q_ball && q.v[0] == B.v[0] && q.v[1] == B.v[1] && q.v[2] == B.v[2] && std::fabs(q.v[3]) >= std::fabs(B.v[3])) continue;
+                    if (q_ball) {  // sphere against ball, exactly: the surface of q comes within |dist - |r_q|| of the centre
+                        double dist2 = 0.0;
+                        for (int k = 0; k < 3; ++k) dist2 += ((double)q.v[k] - (double)B.v[k]) * ((double)q.v[k] - (double)B.v[k]);
+                        if (std::fabs(std::sqrt(dist2) - std::fabs((double)q.v[3])) >= r) continue;  // (the coincident shell: == r)
+                    }
                 }
                 clear = false;
             }

@@ -155,6 +155,7 @@ uint64_t emul_render(void* h, const RtCamera* cam, const RtParams* p, int32_t th
 }
 
 uint32_t emul_clear_media(void* h) { return ((EmulScene*)h)->flat.clear_media; }
+uint32_t emul_scene_features(void* h) { return ((EmulScene*)h)->flat.features; }
 
 // The wavefront slot functions (wf_init_pixel_sample, closest hit, wf_shade) driven path by path on host threads, as the
 // persistent kernel drives them — with `use_chain`, paths inside a clear medium advance with wf_chain_step instead of a

@@ -97,6 +97,8 @@ def emul():
         L.emul_render.argtypes = [C.c_void_p, C.POINTER(abi.RtCamera), C.POINTER(abi.RtParams), C.c_int32, C.c_void_p]
         L.emul_clear_media.restype = C.c_uint32
         L.emul_clear_media.argtypes = [C.c_void_p]
+        L.emul_scene_features.restype = C.c_uint32
+        L.emul_scene_features.argtypes = [C.c_void_p]
         L.emul_render_slots.argtypes = [C.c_void_p, C.POINTER(abi.RtCamera), C.POINTER(abi.RtParams), C.c_int32, C.c_int32, C.c_void_p, C.c_void_p]
         _emul = L
     return _emul
@@ -223,6 +225,10 @@ class EmulScene:
     @property
     def clear_media(self):
         return int(emul().emul_clear_media(self.h))
+
+    @property
+    def features(self):
+        return int(emul().emul_scene_features(self.h))
 
     def render_slots(self, cam, width, height, spp, chain, max_depth=50, seed=42, threads=0):
         """the wavefront slot functions driven path by path (fixed-point sums, rays, chain steps); chain=True advances
