@@ -54,6 +54,37 @@ struct PsCounters {
     unsigned long long next_path, total_paths, rays;
 };
 
+// ---- chain queues (CHAINQ instances).  A path whose ray starts inside a CLEAR medium and whose next event lies inside it
+// too (wf_chain_eligible) LEAVES the persistent kernel: its record goes to the chain queue in global memory, its slot is
+// free.  chain_kernel — a small kernel of its own, so that its code does not share the 32 KB instruction cache with this
+// one — hops such paths from event to event (wf_chain_step) until they leave the medium or end, and
+// writes the ones that leave to the exit queue, which the NEXT launch of the persistent kernel consumes before it starts
+// new camera paths.  One record = PQ_REC words, SoA over the queue: origin, direction, beta, t, pixel, sample, flags, code
+// (the pre-sampled event of the ray: what WfSlot.D.x / D.y hold).
+enum { PQ_REC = 14 };
+struct ChainCounters {
+    unsigned int chain_count, chain_taken;  // records pushed by the persistent kernel / reserved by chain_kernel
+    unsigned int exit_count, exit_taken;    // records pushed by chain_kernel / reserved by the next persistent launch
+    unsigned int chain_dropped, pad;        // pushes that found the chain queue full (the path then stays in the kernel)
+};
+struct PsChainIO {
+    float* chain;  // [PQ_REC][cap]
+    float* exitq;  // [PQ_REC][cap]
+    ChainCounters* cc;
+    unsigned int cap;
+};
+__device__ __forceinline__ void queue_store(float* q, unsigned int cap, unsigned int i, const WfSlot& s) {
+    q[0 * cap + i] = s.A.x, q[1 * cap + i] = s.A.y, q[2 * cap + i] = s.A.z, q[3 * cap + i] = s.B.x, q[4 * cap + i] = s.B.y, q[5 * cap + i] = s.B.z;
+    q[6 * cap + i] = s.C.x, q[7 * cap + i] = s.C.y, q[8 * cap + i] = s.C.z, q[9 * cap + i] = s.D.x;
+    q[10 * cap + i] = s.A.w, q[11 * cap + i] = s.C.w, q[12 * cap + i] = s.B.w, q[13 * cap + i] = s.D.y;
+}
+__device__ __forceinline__ void queue_load(const float* q, unsigned int cap, unsigned int i, WfSlot& s) {
+    s.A = f4(q[0 * cap + i], q[1 * cap + i], q[2 * cap + i], q[10 * cap + i]);
+    s.B = f4(q[3 * cap + i], q[4 * cap + i], q[5 * cap + i], q[12 * cap + i]);
+    s.C = f4(q[6 * cap + i], q[7 * cap + i], q[8 * cap + i], q[11 * cap + i]);
+    s.D = f4(q[9 * cap + i], q[13 * cap + i], as_float(0xFFFFFFFFu), 0.f);  // origin primitive: none (the ray starts at a medium event)
+}
+
 #define PS_VARIANTS 12
 #define PS_DEFAULT_LAYOUT 4    // RT_BVH_LAYOUT / RtParams.bvh_layout override
 #define PS_DEFAULT_VARIANT 2   // index into kVariants for the 4-wide layout; RT_PS_VARIANT overrides
@@ -61,6 +92,7 @@ struct PsCounters {
 struct PersistState {
     PsCounters* ctr = nullptr;
     std::map<const void*, int> blocks;  // resident grid of each kernel instance launched so far
+    PsChainIO io = {nullptr, nullptr, nullptr, 0u};  // chain / exit queues of the CHAINQ instances (allocated at the first such launch)
 };
 
 // One camera path = one record of PS_REC words in shared memory, SoA over the block's threads (conflict-free):
@@ -150,7 +182,56 @@ __device__ __forceinline__ float warp_turbulence(const float* __restrict__ vec, 
     return fabsf(acc);
 }
 
-__global__ void ps_reset_kernel(PsCounters* c, unsigned long long total) { c->next_path = 0, c->total_paths = total, c->rays = 0; }
+__global__ void ps_reset_kernel(PsCounters* c, unsigned long long total, ChainCounters* cc) {
+    c->next_path = 0, c->total_paths = total, c->rays = 0;
+    if (cc) cc->exit_taken = 0u, cc->chain_count = 0u;  // (exit_count: what the previous chain_kernel left)
+}
+__global__ void chain_reset_kernel(ChainCounters* cc) { cc->chain_taken = 0u, cc->exit_count = 0u; }
+
+// The chain paths of one launch of the persistent kernel, hopped to their end.  Persistent warps: every lane owns one
+// record at a time; lanes whose path left the medium (-> exit queue) or ended take the next records of the queue, 32 lanes'
+// worth of reservations per atomic.
+#define CHAIN_THREADS 256
+__global__ void __launch_bounds__(CHAIN_THREADS) chain_kernel(DSceneView S, DRenderParams P, PsChainIO io, unsigned long long* __restrict__ rays_out) {
+    const unsigned int lane = threadIdx.x & 31u;
+    const unsigned int lt_mask = (1u << lane) - 1u;
+    const unsigned int n = min(io.cc->chain_count, io.cap);
+    WfSlot s;
+    s.A = s.B = s.C = s.D = f4(0.f, 0.f, 0.f, 0.f);
+    bool active = false, drained = false;
+    unsigned int n_rays = 0u;
+    for (;;) {
+        // refill the idle lanes
+        const unsigned int m_idle = __ballot_sync(0xffffffffu, !active);
+        if (!drained && (__popc(m_idle) >= 8 || m_idle == 0xffffffffu)) {  // (one atomic per 8+ records, not per record)
+            const unsigned int want = (unsigned int)__popc(m_idle);
+            unsigned int base = 0u;
+            if (lane == 0) base = atomicAdd(&io.cc->chain_taken, want);
+            base = __shfl_sync(0xffffffffu, base, 0);
+            const unsigned int have = base < n ? min(want, n - base) : 0u;
+            if (have < want) drained = true;
+            const unsigned int rank = (unsigned int)__popc(m_idle & lt_mask);
+            if (!active && rank < have) queue_load(io.chain, io.cap, base + rank, s), active = true;
+        }
+        if (__ballot_sync(0xffffffffu, active) == 0u) break;
+        int rc = 1;
+        if (active) {
+            n_rays += 1u;
+            rc = wf_chain_step<MEDIA_FAST>(S, P, s);
+            if (rc != 1) active = false;
+        }
+        const unsigned int m_exit = __ballot_sync(0xffffffffu, rc == 2);
+        if (m_exit) {
+            const int first = __ffs((int)m_exit) - 1;
+            unsigned int base = 0u;
+            if ((int)lane == first) base = atomicAdd(&io.cc->exit_count, (unsigned int)__popc(m_exit));
+            base = __shfl_sync(0xffffffffu, base, first);
+            if (rc == 2) queue_store(io.exitq, io.cap, base + (unsigned int)__popc(m_exit & lt_mask), s);  // (never more exits than chain records: fits)
+        }
+    }
+    for (int off = 16; off > 0; off >>= 1) n_rays += __shfl_down_sync(0xffffffffu, n_rays, off);
+    if (lane == 0 && n_rays) atomicAdd(rays_out, (unsigned long long)n_rays);
+}
 
 // phase statistics of a debug launch (RT_PS_STATS=1): warp-level step counts and the lanes that were useful in them
 enum { PSS_SHADE_PHASES, PSS_SHADE_ACT, PSS_SHADE_DONE, PSS_SHADE_ONPARK, PSS_EXT_PHASES, PSS_INNER_ITERS, PSS_INNER_LANES, PSS_LEAF_STEPS,
@@ -214,10 +295,10 @@ __device__ __forceinline__ uint2 chain_phase(float* pool, const SV& S, const DRe
 // Dynamic shared memory: [pool NS x PS_REC x NT floats][stack SD x NT keys][nodes4][prims].
 #define PS_SCENE_NODES 1
 #define PS_SCENE_PRIMS 2
-template <bool STATS, bool WIDE, int SD, int NT, int SCENE, int MEDIA, int NS, bool CHAIN, uint32_t FEAT>
+template <bool STATS, bool WIDE, int SD, int NT, int SCENE, int MEDIA, int NS, bool CHAIN, uint32_t FEAT, bool CHAINQ>
 __device__ __forceinline__ void persist_body(const DSceneView& S_, const DCamera& cam, const DRenderParams& P, PsCounters* __restrict__ ctr,
                                              AccumFx* __restrict__ accum, unsigned long long* __restrict__ rays_out, unsigned int chunk_size,
-                                             unsigned long long* __restrict__ stats, const PsTune& tune) {
+                                             unsigned long long* __restrict__ stats, const PsTune& tune, const PsChainIO& io) {
     const SceneViewF<FEAT>& S = static_cast<const SceneViewF<FEAT>&>(S_);  // same record; SV::feat = what the scene can contain (rt_types.h)
     unsigned int st_[PSS_COUNT];
     if (STATS)
@@ -284,6 +365,7 @@ __device__ __forceinline__ void persist_body(const DSceneView& S_, const DCamera
     unsigned long long chunk_next = 0, chunk_end = 0;
     uint32_t chunk_pixel = 0, chunk_sample = 0;  // (pixel, sample) of path chunk_next
     bool exhausted = false;
+    bool exits_done = !CHAINQ;  // CHAINQ: the exit queue of the previous launch is served before new camera paths
     unsigned int n_rays = 0;
     // (scenes that need the general media sampler keep to the shade phase: with the out-of-line sampler inside it the chain
     // phase would cost that kernel instance 480 B more spills)
@@ -390,7 +472,22 @@ __device__ __forceinline__ void persist_body(const DSceneView& S_, const DCamera
             }
             // regenerate: the next camera paths of the job, handed out in reservation order
             bool need = act && !alive;
+            bool from_exit = false;
             unsigned int m_need = __ballot_sync(0xffffffffu, need);
+            if (CHAINQ && !exits_done && m_need) {  // paths that chain_kernel took out of a clear medium after the previous launch
+                const unsigned int n_exit = min(io.cc->exit_count, io.cap);
+                const unsigned int want = (unsigned int)__popc(m_need);
+                unsigned int base = 0u;
+                if (lane == 0) base = atomicAdd(&io.cc->exit_taken, want);
+                base = __shfl_sync(0xffffffffu, base, 0);
+                const unsigned int have = base < n_exit ? min(want, n_exit - base) : 0u;
+                if (have < want) exits_done = true;
+                if (need && (unsigned int)__popc(m_need & lt_mask) < have) {
+                    queue_load(io.exitq, io.cap, base + (unsigned int)__popc(m_need & lt_mask), s);  // ray + its pre-sampled event: ready as it is
+                    alive = true, need = false, from_exit = true;
+                }
+                m_need = __ballot_sync(0xffffffffu, need);
+            }
             while (m_need) {
                 const unsigned int avail = (unsigned int)(chunk_end - chunk_next);
                 if (avail == 0u) {
@@ -430,15 +527,47 @@ __device__ __forceinline__ void persist_body(const DSceneView& S_, const DCamera
                 m_need = __ballot_sync(0xffffffffu, need);
             }
             // survivors and fresh camera paths alike: media event of the new ray, then "ready"
-            if (act) {
-                if (alive) {
-                    const int code_shaded = __float_as_int(s.D.y);  // the hit this path was shaded at (wf_shade_core leaves it; a fresh camera path: 0)
+            if constexpr (!CHAINQ) {
+                // survivors and fresh camera paths alike: media event of the new ray, then "ready"
+                if (act) {
+                    if (alive) {
+                        const int code_shaded = __float_as_int(s.D.y);  // the hit this path was shaded at (wf_shade_core leaves it; a fresh camera path: 0)
+                        wf_presample_media<MEDIA>(S, P, s, segment_next);
+                        rec_store<NT>(pool, s_work, s);
+                        // a medium event of a clear medium followed by another one: the path hops on in the chain phase
+                        stat = slot_set(stat, s_work, (CHAIN && chain_on && wf_chain_eligible(S, code_shaded, s)) ? ST_CHAIN : ST_READY);
+                    } else {
+                        stat = slot_set(stat, s_work, ST_EMPTY);
+                    }
+                }
+            } else {
+                // the same, except that a path which can hop on without a surface search (a medium event of a clear medium followed
+                // by another one) leaves the kernel for chain_kernel: its record goes to the chain queue, its slot is free
+                bool eligible = false;
+                if (act && alive && !from_exit) {  // (a path from the exit queue brings its pre-sampled event along)
+                    const int code_shaded = __float_as_int(s.D.y);
                     wf_presample_media<MEDIA>(S, P, s, segment_next);
-                    rec_store<NT>(pool, s_work, s);
-                    // a medium event of a clear medium followed by another one: the path hops on in the chain phase
-                    stat = slot_set(stat, s_work, (CHAIN && chain_on && wf_chain_eligible(S, code_shaded, s)) ? ST_CHAIN : ST_READY);
-                } else {
-                    stat = slot_set(stat, s_work, ST_EMPTY);
+                    eligible = wf_chain_eligible(S, code_shaded, s);
+                }
+                const unsigned int m_el = __ballot_sync(0xffffffffu, eligible);
+                if (m_el) {
+                    const int first = __ffs((int)m_el) - 1;
+                    unsigned int base = 0u;
+                    if ((int)lane == first) base = atomicAdd(&io.cc->chain_count, (unsigned int)__popc(m_el));
+                    base = __shfl_sync(0xffffffffu, base, first);
+                    const unsigned int idx = base + (unsigned int)__popc(m_el & lt_mask);
+                    if (eligible) {
+                        if (idx < io.cap) queue_store(io.chain, io.cap, idx, s), alive = false;
+                        else atomicAdd(&io.cc->chain_dropped, 1u);  // queue full: the path stays here, as any other
+                    }
+                }
+                if (act) {
+                    if (alive) {
+                        rec_store<NT>(pool, s_work, s);
+                        stat = slot_set(stat, s_work, ST_READY);
+                    } else {
+                        stat = slot_set(stat, s_work, ST_EMPTY);
+                    }
                 }
             }
             continue;
@@ -558,17 +687,22 @@ __device__ __forceinline__ void persist_body(const DSceneView& S_, const DCamera
 #undef PS_STAT
 }
 
-template <bool STATS, bool WIDE, int SD, int NT, int SCENE, int MEDIA, int NS, bool CHAIN, uint32_t FEAT>
+template <bool STATS, bool WIDE, int SD, int NT, int SCENE, int MEDIA, int NS, bool CHAIN, uint32_t FEAT, bool CHAINQ = false>
 __global__ void __launch_bounds__(NT, (STATS || NT > 128) ? 1 : PS_MIN_BLOCKS) persist_kernel(DSceneView S, DCamera cam, DRenderParams P, PsCounters* __restrict__ ctr,
                                                              AccumFx* __restrict__ accum, unsigned long long* __restrict__ rays_out,
-                                                             unsigned int chunk_size, unsigned long long* __restrict__ stats, PsTune tune) {
-    persist_body<STATS, WIDE, SD, NT, SCENE, MEDIA, NS, CHAIN, FEAT>(S, cam, P, ctr, accum, rays_out, chunk_size, stats, tune);
+                                                             unsigned int chunk_size, unsigned long long* __restrict__ stats, PsTune tune, PsChainIO io) {
+    persist_body<STATS, WIDE, SD, NT, SCENE, MEDIA, NS, CHAIN, FEAT, CHAINQ>(S, cam, P, ctr, accum, rays_out, chunk_size, stats, tune, io);
 }
 
 // ---------------------------------------------------------------------------------------------------------------
 void free_persist(RtScene* s) {
     if (!s->ps) return;
     rtb::cache_free(s->ps->ctr, sizeof(PsCounters));
+    if (s->ps->io.cc) {
+        rtb::cache_free(s->ps->io.chain, (size_t)PQ_REC * s->ps->io.cap * sizeof(float));
+        rtb::cache_free(s->ps->io.exitq, (size_t)PQ_REC * s->ps->io.cap * sizeof(float));
+        rtb::cache_free(s->ps->io.cc, sizeof(ChainCounters));
+    }
     delete s->ps;
     s->ps = nullptr;
 }
@@ -577,7 +711,7 @@ bool persist_supports(const RtScene* s, const RtParams* p) { return p->max_depth
 
 namespace {
 
-typedef void (*PersistFn)(DSceneView, DCamera, DRenderParams, PsCounters*, AccumFx*, unsigned long long*, unsigned int, unsigned long long*, PsTune);
+typedef void (*PersistFn)(DSceneView, DCamera, DRenderParams, PsCounters*, AccumFx*, unsigned long long*, unsigned int, unsigned long long*, PsTune, PsChainIO);
 struct Variant {
     int layout, smem_stack, threads, scene, slots;
     PersistFn fn, fn_general, fn_stats;  // fn: scenes with <= 4 single-primitive media; fn_general: any media (rt_device.cuh: sample_media)
@@ -623,25 +757,39 @@ struct FeatInstance {
     uint32_t mask;
     int threads;
     PersistFn fn;
+    PersistFn fn_q;  // the same with the chain queues (CHAINQ), for scenes with clear media; nullptr: none built
     const char* name;
 };
 #define PS_FEAT_INSTANCE(mask, nt) mask, nt, persist_kernel<false, true, 0, nt, 0, MEDIA_FAST, 2, false, mask>
+#define PS_FEAT_INSTANCE_Q(mask, nt) persist_kernel<false, true, 0, nt, 0, MEDIA_FAST, 2, false, mask, true>
 constexpr uint32_t kFeatSpheres = F_SPHERE | F_BIG;                                                           // random (C1, C2), simple
 constexpr uint32_t kFeatBoxes = F_BOX | F_INSTBOX | F_INSTANCE | F_MEDIA | F_BOXMEDIA;                        // cornell_box, cornell_smoke (C3)
 constexpr uint32_t kFeatFinal = F_SPHERE | F_BOX | F_INSTANCE | F_BIG | F_MEDIA | F_NOISE | F_IMAGE;          // final_scene (C4, C5)
 const FeatInstance kFeatInstances[] = {
-    {PS_FEAT_INSTANCE(kFeatSpheres, 768), "spheres"},
-    {PS_FEAT_INSTANCE(kFeatBoxes, 768), "boxes, instances, box media"},
-    {PS_FEAT_INSTANCE(kFeatFinal, 768), "spheres, world-space boxes, sphere media, noise and image textures"},
+    {PS_FEAT_INSTANCE(kFeatSpheres, 768), nullptr, "spheres"},
+    {PS_FEAT_INSTANCE(kFeatBoxes, 768), PS_FEAT_INSTANCE_Q(kFeatBoxes, 768), "boxes, instances, box media"},
+    {PS_FEAT_INSTANCE(kFeatFinal, 768), PS_FEAT_INSTANCE_Q(kFeatFinal, 768), "spheres, world-space boxes, sphere media, noise and image textures"},
+    {PS_FEAT_INSTANCE(F_ALL, 768), PS_FEAT_INSTANCE_Q(F_ALL, 768), "everything"},
 };
-PersistFn pick_feature_instance(const RtScene* s, int vi, PersistFn generic, int* threads) {
+// Chain queues: OPT-IN (RT_PS_CHAINQ=1), for scenes with clear media (FlatScene.clear_media) and the fast media sampler.
+// Exact (identical images and ray counts, also with queues far too small) and measured (profiles/r2_chain_phase.txt,
+// section 6): on C4 the main launch of the persistent kernel gets 37 % shorter, but what it saves in total is 8 % — the chain
+// segments had been cheap riders of its phases — and chain_kernel costs 10 %: 2318 against 2313 Mpaths/s; C3 loses 19 %.
+bool want_chain_queues(const RtScene* s) {
+    if (s->flat.clear_media == 0u || s->view.media_general) return false;
+    if (const char* e = getenv("RT_PS_CHAINQ")) return atoi(e) != 0;
+    return false;
+}
+PersistFn pick_feature_instance(const RtScene* s, int vi, PersistFn generic, int* threads, bool* queues) {
+    *queues = false;
     if (vi != PS_DEFAULT_VARIANT || s->view.media_general) return generic;
-    if (const char* e = getenv("RT_PS_FEAT"))
-        if (atoi(e) == 0) return generic;
+    bool specialise = true;
+    if (const char* e = getenv("RT_PS_FEAT")) specialise = atoi(e) != 0;
+    const bool q = want_chain_queues(s);
     for (const FeatInstance& f : kFeatInstances)
-        if ((s->flat.features & ~f.mask) == 0u) {
-            *threads = f.threads;
-            return f.fn;
+        if ((s->flat.features & ~f.mask) == 0u && (specialise || f.mask == F_ALL) && (!q || f.fn_q)) {
+            *threads = f.threads, *queues = q;
+            return q ? f.fn_q : f.fn;
         }
     return generic;
 }
@@ -681,7 +829,9 @@ void persist_preload(const RtScene* s) {
     cudaFuncAttributes fa;
     const int vi = pick_variant(s, &p);
     int nt = V.threads;
-    if (cudaFuncGetAttributes(&fa, s->view.media_general ? V.fn_general : pick_feature_instance(s, vi, V.fn, &nt)) != cudaSuccess) cudaGetLastError();
+    bool queues = false;
+    if (cudaFuncGetAttributes(&fa, s->view.media_general ? V.fn_general : pick_feature_instance(s, vi, V.fn, &nt, &queues)) != cudaSuccess) cudaGetLastError();
+    if (queues && cudaFuncGetAttributes(&fa, chain_kernel) != cudaSuccess) cudaGetLastError();
 }
 
 int launch_persist(RtScene* s, const DCamera& cam, const RtParams* p, int begin, int count, AccumFx* d_accum, cudaStream_t stream, RtProgressFn cb,
@@ -697,7 +847,9 @@ int launch_persist(RtScene* s, const DCamera& cam, const RtParams* p, int begin,
     const int vi = pick_variant(s, p);
     const Variant& V = kVariants[vi];
     int NT = V.threads;
-    const PersistFn kernel = s->view.media_general ? V.fn_general : pick_feature_instance(s, vi, V.fn, &NT);
+    bool queues = false;
+    const PersistFn kernel = s->view.media_general ? V.fn_general : pick_feature_instance(s, vi, V.fn, &NT, &queues);
+    if (getenv("RT_PS_STATS")) queues = false;  // (the statistics instance has no queues)
     const size_t smem = variant_smem(V, s) / V.threads * NT;  // (every term of it is per thread for the variant feature instances exist for)
     const void* const key = getenv("RT_PS_STATS") ? (const void*)V.fn_stats : (const void*)kernel;
     if (w->blocks.find(key) == w->blocks.end()) {
@@ -721,7 +873,42 @@ int launch_persist(RtScene* s, const DCamera& cam, const RtParams* p, int begin,
     const unsigned long long npix = (unsigned long long)p->width * p->height;
     // one launch = up to 2^29 camera paths when progress is reported (a quarter of a second on C4), 2^33 otherwise: every
     // launch ends with a tail in which the longest paths run on a mostly idle machine
-    const int samples_per_launch = (int)std::min<unsigned long long>(1u << 30, std::max<unsigned long long>(1, (1ull << (cb ? 29 : 33)) / npix));
+    int samples_per_launch = (int)std::min<unsigned long long>(1u << 30, std::max<unsigned long long>(1, (1ull << (cb ? 29 : 33)) / npix));
+    // Chain queues: one launch = 2^27 camera paths (RT_PS_CHAINQ_LOG2_PATHS), and queues of 2^24 records (RT_PS_CHAINQ_LOG2_CAP; 2 x
+    // 896 MB) — final_scene pushes ~0.1 records per path; a push that finds the queue full leaves the path in the kernel.
+    PsChainIO io = {nullptr, nullptr, nullptr, 0u};
+    int chain_blocks = 0;
+    if (queues) {
+        int log2_paths = 27, log2_cap = 24;
+        if (const char* e = getenv("RT_PS_CHAINQ_LOG2_PATHS")) log2_paths = std::max(10, std::min(33, atoi(e)));
+        if (const char* e = getenv("RT_PS_CHAINQ_LOG2_CAP")) log2_cap = std::max(8, std::min(28, atoi(e)));
+        samples_per_launch = (int)std::min<unsigned long long>((unsigned long long)samples_per_launch, std::max<unsigned long long>(1, (1ull << log2_paths) / npix));
+        const unsigned int cap = 1u << log2_cap;
+        if (w->io.cc && w->io.cap != cap) {  // another capacity asked for: start over
+            rtb::cache_free(w->io.chain, (size_t)PQ_REC * w->io.cap * sizeof(float)), rtb::cache_free(w->io.exitq, (size_t)PQ_REC * w->io.cap * sizeof(float));
+            rtb::cache_free(w->io.cc, sizeof(ChainCounters));
+            w->io = PsChainIO{nullptr, nullptr, nullptr, 0u};
+        }
+        if (!w->io.cc) {
+            CU_TRY(rtb::cache_malloc((void**)&w->io.chain, (size_t)PQ_REC * cap * sizeof(float)));
+            CU_TRY(rtb::cache_malloc((void**)&w->io.exitq, (size_t)PQ_REC * cap * sizeof(float)));
+            CU_TRY(rtb::cache_malloc((void**)&w->io.cc, sizeof(ChainCounters)));
+            w->io.cap = cap;
+        }
+        io = w->io;
+        CU_TRY(cudaMemsetAsync(io.cc, 0, sizeof(ChainCounters), stream));
+        int per_sm = 0, sms = 0;
+        CU_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, chain_kernel, CHAIN_THREADS, 0));
+        CU_TRY(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, s->device));
+        chain_blocks = std::max(1, per_sm) * std::max(1, sms);
+    }
+    PsTune tune = {PS_WORK, PS_STALL, PS_LEAVE, PS_MIN_DESCEND, PS_CHAIN_TRIG, PS_CHAIN_MIN};
+    if (const char* e = getenv("RT_PS_CHAIN_TRIG")) tune.chain_trig = atoi(e);
+    if (const char* e = getenv("RT_PS_CHAIN_MIN")) tune.chain_min = std::max(1, atoi(e));
+    if (const char* e = getenv("RT_PS_WORK")) tune.work = atoi(e);
+    if (const char* e = getenv("RT_PS_STALL")) tune.stall = atoi(e);
+    if (const char* e = getenv("RT_PS_LEAVE")) tune.leave = atoi(e);
+    if (const char* e = getenv("RT_PS_DESCEND")) tune.descend = atoi(e);
     int done = 0;
     while (done < count) {
         int samples = std::min(count - done, samples_per_launch);
@@ -732,19 +919,12 @@ int launch_persist(RtScene* s, const DCamera& cam, const RtParams* p, int begin,
         unsigned long long per_warp = total / ((unsigned long long)blocks * (NT / 32) * 4ull);
         unsigned int chunk = (unsigned int)std::min<unsigned long long>(PS_CHUNK, std::max<unsigned long long>(32ull, per_warp));
         chunk = (unsigned int)std::min<unsigned long long>(chunk, std::max<unsigned long long>(1ull, npix));
-        ps_reset_kernel<<<1, 1, 0, stream>>>(w->ctr, total);
-        PsTune tune = {PS_WORK, PS_STALL, PS_LEAVE, PS_MIN_DESCEND, PS_CHAIN_TRIG, PS_CHAIN_MIN};
-        if (const char* e = getenv("RT_PS_CHAIN_TRIG")) tune.chain_trig = atoi(e);
-        if (const char* e = getenv("RT_PS_CHAIN_MIN")) tune.chain_min = std::max(1, atoi(e));
-        if (const char* e = getenv("RT_PS_WORK")) tune.work = atoi(e);
-        if (const char* e = getenv("RT_PS_STALL")) tune.stall = atoi(e);
-        if (const char* e = getenv("RT_PS_LEAVE")) tune.leave = atoi(e);
-        if (const char* e = getenv("RT_PS_DESCEND")) tune.descend = atoi(e);
+        ps_reset_kernel<<<1, 1, 0, stream>>>(w->ctr, total, io.cc);
         if (getenv("RT_PS_STATS")) {  // debug: phase statistics on stderr (slower kernel; never used by the bench)
             unsigned long long* d_stats = nullptr;
             CU_TRY(cudaMalloc(&d_stats, PSS_COUNT * sizeof(unsigned long long)));
             CU_TRY(cudaMemsetAsync(d_stats, 0, PSS_COUNT * sizeof(unsigned long long), stream));
-            V.fn_stats<<<blocks, NT, smem, stream>>>(s->view, cam, P, w->ctr, d_accum, s->d_rays, chunk, d_stats, tune);
+            V.fn_stats<<<blocks, NT, smem, stream>>>(s->view, cam, P, w->ctr, d_accum, s->d_rays, chunk, d_stats, tune, io);
             unsigned long long h[PSS_COUNT];
             CU_TRY(cudaMemcpyAsync(h, d_stats, sizeof h, cudaMemcpyDeviceToHost, stream));
             CU_TRY(cudaStreamSynchronize(stream));
@@ -756,15 +936,38 @@ int launch_persist(RtScene* s, const DCamera& cam, const RtParams* p, int begin,
             for (int k = 0; k < PSS_COUNT; ++k) fprintf(stderr, " %s=%llu", names[k], h[k]);
             fprintf(stderr, "\n");
         } else {
-            kernel<<<blocks, NT, smem, stream>>>(s->view, cam, P, w->ctr, d_accum, s->d_rays, chunk, nullptr, tune);
+            kernel<<<blocks, NT, smem, stream>>>(s->view, cam, P, w->ctr, d_accum, s->d_rays, chunk, nullptr, tune, io);
         }
         CU_TRY(cudaGetLastError());
         *launches += 2;
         done += samples;
+        if (queues) {  // the chain paths of this launch, hopped to their end; those that leave their medium wait for the next launch
+            chain_reset_kernel<<<1, 1, 0, stream>>>(io.cc);
+            chain_kernel<<<chain_blocks, CHAIN_THREADS, 0, stream>>>(s->view, P, io, s->d_rays);
+            CU_TRY(cudaGetLastError());
+            *launches += 2;
+        }
         if (cb) {
             CU_TRY(cudaStreamSynchronize(stream));
             cb(done, count, user);
         }
+    }
+    // drain: launches without new camera paths until no path is left in either queue (each takes a tenth of the previous one's)
+    for (int round = 0; queues && round < 1024; ++round) {
+        ChainCounters h;
+        CU_TRY(cudaMemcpyAsync(&h, io.cc, sizeof h, cudaMemcpyDeviceToHost, stream));
+        CU_TRY(cudaStreamSynchronize(stream));
+        const unsigned int n_exit = std::min(h.exit_count, io.cap);
+        if (getenv("RT_PS_CHAINQ_VERBOSE")) fprintf(stderr, "chain queues: drain round %d, %u exits, %u pushes dropped so far\n", round, n_exit, h.chain_dropped);
+        if (n_exit == 0u) break;
+        DRenderParams P = device_params(p, begin + count, 1, 1);
+        const int blocks = (int)std::min<unsigned long long>((unsigned long long)w->blocks[key], ((unsigned long long)n_exit + 2 * NT - 1) / (2 * NT));
+        ps_reset_kernel<<<1, 1, 0, stream>>>(w->ctr, 0ull, io.cc);
+        kernel<<<blocks, NT, smem, stream>>>(s->view, cam, P, w->ctr, d_accum, s->d_rays, 32u, nullptr, tune, io);
+        chain_reset_kernel<<<1, 1, 0, stream>>>(io.cc);
+        chain_kernel<<<chain_blocks, CHAIN_THREADS, 0, stream>>>(s->view, P, io, s->d_rays);
+        CU_TRY(cudaGetLastError());
+        *launches += 4;
     }
     return RT_OK;
 }

@@ -143,3 +143,23 @@ def test_chain_instance_on_device(name, monkeypatch):
     assert abs(st0["rays"] - st1["rays"]) <= 1e-3 * st0["rays"]
     close = np.isclose(a0, a1, rtol=1e-4, atol=1e-4 * a0.mean()).all(axis=2)
     assert close.mean() > 0.99, close.mean()
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("name", ["final_scene", "cornell_smoke"])
+@pytest.mark.parametrize("log2_paths,log2_cap", [(27, 24), (14, 8)])
+def test_chain_queues_on_device(name, log2_paths, log2_cap, monkeypatch):
+    """the opt-in second kernel for the paths inside clear media (RT_PS_CHAINQ=1: chain queue -> chain_kernel -> exit queue ->
+    next launch, drain rounds at the end) renders what the single kernel renders — also with launches of 2^14 paths and queues
+    of 256 records, where most pushes find the queue full and the paths stay in the kernel"""
+    W, spp = 96, 24
+    rgb0, a0, st0 = _render(name, 1.0, W, spp)
+    monkeypatch.setenv("RT_PS_CHAINQ", "1")
+    monkeypatch.setenv("RT_PS_CHAINQ_LOG2_PATHS", str(log2_paths))
+    monkeypatch.setenv("RT_PS_CHAINQ_LOG2_CAP", str(log2_cap))
+    rgb1, a1, st1 = _render(name, 1.0, W, spp)
+    assert st0["paths"] == st1["paths"]
+    assert abs(st0["rays"] - st1["rays"]) <= 1e-4 * st0["rays"]
+    assert st1["kernel_launches"] > st0["kernel_launches"]
+    close = np.isclose(a0, a1, rtol=1e-5, atol=1e-5 * a0.mean()).all(axis=2)
+    assert close.mean() > 0.999, close.mean()
