@@ -347,6 +347,8 @@ __device__ __forceinline__ void persist_body(const DSceneView& S_, const DCamera
     int hit = -1, origin_prim = -1, origin_face = 0, cur = DONE, sp = 0;
     StackEntry stack[WIDE ? 1 : RTB_BVH_STACK];  // binary tree: (node link, entry distance of its box), see stack_pop
     uint32_t lstack[WIDE ? RTB_WIDE_STACK : 1];  // 4-wide tree: the keys above the shared-memory levels
+    // (tried: the top of the stack mirrored in a register so that a pop does not wait for its local-memory load — one register
+    // more, 12 B more spills, -2 ... -3 % on C2 - C4; gpurun_out/ab_stacktop.txt)
     auto push4 = [&](uint32_t k) {
         if (SD > 0 && sp < SD) sstack[sp * NT + threadIdx.x] = k;
         else lstack[sp - SD] = k;
