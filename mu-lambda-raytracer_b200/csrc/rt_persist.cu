@@ -105,6 +105,8 @@ enum { R_OX, R_OY, R_OZ, R_DX, R_DY, R_DZ, R_BR, R_BG, R_BB, R_T, R_PIXEL, R_SAM
 // field `f` of record `slot` of the calling thread; the pool is [NS][PS_REC][NT] floats at the start of shared memory
 #define POOL(slot, f) pool[((slot) * PS_REC + (f)) * NT + threadIdx.x]
 
+// (tried: one 4-bit SET of slots per status, slot_find = a bit-field extract and a find-first-set — FLO is a slow-pipe
+// instruction: -0.8 % on C4, -2.4 % on C3; gpurun_out/ab_slots.txt)
 __device__ __forceinline__ int slot_status(unsigned int stat, int s) { return (int)((stat >> (4 * s)) & 15u); }
 __device__ __forceinline__ unsigned int slot_set(unsigned int stat, int s, int st) { return (stat & ~(15u << (4 * s))) | ((unsigned int)st << (4 * s)); }
 template <int NS>
