@@ -4,16 +4,23 @@
 // It replaces Renderer::render / render_pixel / trace_internal (src/raytrace.rs:172-198, :79-101).  Every lane owns TWO
 // camera paths, both as records in shared memory; registers hold the context of the one being traversed (ray, closest
 // hit so far, cursor), the other waits to be shaded or holds a fresh ray.  The warp alternates between
-//   extend  : while-while BVH traversal of the paths in flight (32-byte nodes, 128-bit __ldg, short stack of
-//             (node, entry distance) pairs); lanes vote between the inner-node loop and a leaf step, as in wf_extend_kernel;
+//   extend  : while-while traversal of the paths in flight — the 4-wide tree (128-byte nodes, four 256-bit loads, 4-byte
+//             sort / stack keys) or, selectable, the binary tree of 32-byte nodes; lanes vote between the inner-node loop
+//             and a leaf step;
 //   shade   : when enough lanes hold a finished traversal (or an empty slot), those paths are shaded together —
-//             scatter / emit / background, terminated paths deposit beta * radiance with float REDs and are
+//             scatter / emit / background, terminated paths deposit beta * radiance with 64-bit fixed-point REDs and are
 //             regenerated in place from a global camera-path counter (reserved in chunks, one atomic per 256 paths),
 //             the media event of the new ray is pre-sampled — and become "ready" again.
 // A lane whose traversal finishes simply starts on its other, ready path and keeps traversing, so the extend
 // stage runs with (nearly) full warps and the shade stage with (nearly) full warps, without any queue in global memory:
 // HBM only sees the accumulation REDs.  Noise textures are evaluated warp-cooperatively (the 56 gradient terms of
 // the 7-octave turbulence are spread over the lanes) instead of by one lane while 31 wait.
+//
+// The kernel's speed hangs on the SM's 32 KB instruction cache: it is instantiated per scene
+// FEATURE SET (FEAT: no code for what a scene cannot contain), and everything that adds code to it is an opt-in instance:
+// the in-kernel chain phase (CHAIN, RT_PS_CHAIN=1) and the chain queues with their own kernel (CHAINQ, RT_PS_CHAINQ=1), two
+// exact but unprofitable ways to advance paths inside "clear" media without a surface search.  tools/sass_footprint.py
+// prints the footprint of an instance by source function.
 #include <cuda_runtime.h>
 
 #include <algorithm>
