@@ -504,15 +504,10 @@ __device__ __forceinline__ void persist_body(const DSceneView& S_, const DCamera
                 if (avail == 0u) {
                     if (exhausted) break;
                     unsigned long long base = 0;
-                    unsigned int cs = chunk_size;
-                    if (lane == 0) {  // guided self-scheduling: towards the end of the job the reservations shrink, so that no warp is
-                                      // left with 256 paths to itself when the others have run out (a job of a few ms notices: C1)
-                        const unsigned long long seen = *reinterpret_cast<volatile unsigned long long*>(&ctr->next_path);
-                        const unsigned long long fair = (total > seen ? total - seen : 0ull) / ((unsigned long long)gridDim.x * (NT / 32) * 2ull);
-                        if (fair < (unsigned long long)cs) cs = fair < 32ull ? 32u : (unsigned int)fair;
-                        base = atomicAdd(&ctr->next_path, (unsigned long long)cs);
-                    }
-                    cs = __shfl_sync(0xffffffffu, cs, 0);  // (+2 % on jobs of 2 - 5 ms, nothing on C4; gpurun_out/ab_c1.txt)
+                    // (tried: guided self-scheduling, reservations that shrink towards the end of the launch: +2 % on jobs of 2 - 5 ms,
+                    // -1.3 % on C4 through the code it adds here; gpurun_out/ab_c1.txt, bench_r2s3.json)
+                    const unsigned int cs = chunk_size;
+                    if (lane == 0) base = atomicAdd(&ctr->next_path, (unsigned long long)cs);
                     base = __shfl_sync(0xffffffffu, base, 0);
                     chunk_next = base < total ? base : total;
                     chunk_end = base + cs < total ? base + cs : total;
