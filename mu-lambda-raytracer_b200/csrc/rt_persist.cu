@@ -34,8 +34,9 @@
 namespace rtb {
 
 #define PS_DONE RTB_TRAVERSAL_DONE
-#define PS_MIN_DESCEND 6   // lanes that must still be descending inner nodes for the inner loop to keep going
-#define PS_LEAVE 8         // lanes that must have finished before the warp leaves the traversal loop (to start them on their other path)
+#define PS_MIN_DESCEND 8   // lanes that must still be descending inner nodes for the inner loop to keep going
+#define PS_LEAVE 12        // lanes that must have finished before the warp leaves the traversal loop (to start them on their other path)
+// (8 / 12 instead of round 1's 6 / 8: +0.5 % on C4, +1.8 % on C2, +-0 on C3 with the final kernel; gpurun_out/ab_tune2.txt)
 #define PS_WORK 28         // lanes with shading / regeneration work pending that trigger a shade phase ...
 #define PS_STALL 14        // ... or lanes that cannot traverse at all (both of their paths wait for the shade phase)
 // resident blocks per SM the kernel is compiled for: 6 = 80 registers with 32 B of spills.  Measured on C4:
