@@ -163,3 +163,16 @@ def test_chain_queues_on_device(name, log2_paths, log2_cap, monkeypatch):
     assert st1["kernel_launches"] > st0["kernel_launches"]
     close = np.isclose(a0, a1, rtol=1e-5, atol=1e-5 * a0.mean()).all(axis=2)
     assert close.mean() > 0.999, close.mean()
+
+
+def test_feature_bits_of_ad_hoc_descriptions():
+    """every kind of node / texture sets its bit — a scene outside every specialised mask falls back to the generic kernel instance"""
+    b = S.DescBuilder()
+    grey = b.lambertian(b.solid(0.5, 0.5, 0.5))
+    chk = b.lambertian(b.checker(b.solid(0, 0, 0), b.solid(1, 1, 1)))
+    items = [b.moving_sphere((0, 0, 0), (0, 1, 0), 0.5, grey), b.sphere((3, 0, 0), 150.0, chk),
+             b.translate((1, 2, 3), b.rotate(1, 30.0, b.block((0, 0, 0), (1, 1, 1), grey))), b.rect(abi.RT_NODE_XZRECT, 0, 1, 0, 1, 5.0, grey),
+             b.medium(b.block((10, 10, 10), (12, 12, 12), grey), 0.1, (1, 1, 1))]
+    es = S.EmulScene(b.finish(b.group(abi.RT_NODE_LIST, items)))
+    assert es.features == F_SPHERE | F_MOVING | F_BIG | F_CHECKER | F_BOX | F_INSTBOX | F_INSTANCE | F_MEDIA | F_BOXMEDIA
+    assert es.clear_media == 0  # conservative: the box of the big sphere AROUND the smoke block overlaps the block's (its surface does not reach it)
